@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- stereo pairs/s of the redtail NVSmall 1025x321 fp32 plugin path on N B200s (one process per GPU).
+
+  python bench.py --gpus 1 --steps 20 --warmup 3                     # this repo's engine
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...                              # the reference's CPU path (oracle port), host cores
+
+A "step" is one pass of the hot path (2-D towers -> cost volume -> 3-D conv / transposed-conv stack -> soft-argmin)
+over one batch of `--batch` synthetic KITTI-shaped stereo pairs per GPU, with the reference's trained NVSmall weights.
+Prints ONE JSON line on rank 0 (contract: see the task statement; DESIGN.md "Measurement" explains every field).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W, MAX_DISP = 321, 1025, 48
+WEIGHTS = os.path.join(ROOT, "tests", "golden", "weights", "nvsmall_fp32.bin")
+# Published by the reference for this net/resolution (other hardware): 450 ms/pair, TensorRT fp32, Titan Xp
+# (stereoDNN/README.md:28).
+PUBLISHED_PAIRS_PER_S = 1000.0 / 450.0
+
+
+def synthetic_pairs(batch, seed=1234):
+    """KITTI-shaped synthetic stereo pairs, float32 [B,3,H,W] in [0,1]: smooth random texture + noise; the right image
+    is the left one warped by a piecewise-planar disparity in [2, 80] px so the cost volume has real structure."""
+    ls, rs = [], []
+    yy, xx = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    for b in range(batch):
+        rng = np.random.default_rng(seed + b)
+        img = np.zeros((3, H, W), np.float32)
+        for c in range(3):
+            acc = np.zeros((H, W), np.float32)
+            for _ in range(6):
+                fx, fy = rng.uniform(0.01, 0.35, 2)
+                acc += rng.uniform(0.3, 1.0) * np.sin(fx * xx + fy * yy + rng.uniform(0, 2 * np.pi))
+            img[c] = (acc - acc.min()) / (acc.max() - acc.min() + 1e-6)
+        left = np.clip(img + 0.05 * rng.uniform(0, 1, img.shape).astype(np.float32), 0, 1).astype(np.float32)
+        disp = np.where(yy > H * 0.55, 2.0 + 78.0 * (yy - H * 0.55) / (H * 0.45), 2.0 + 20.0 * xx / W)
+        xs = np.clip(xx + disp, 0, W - 1)
+        x0 = np.floor(xs).astype(np.int64)
+        x1 = np.minimum(x0 + 1, W - 1)
+        a = (xs - x0).astype(np.float32)
+        rows = np.arange(H)[:, None]
+        right = ((1 - a) * left[:, rows, x0] + a * left[:, rows, x1]).astype(np.float32)
+        ls.append(left)
+        rs.append(right)
+    return np.stack(ls), np.stack(rs)
+
+
+def conv_stack_flops():
+    """Algorithmic FLOPs of the eleven 3-D conv / transposed-conv layers per NVSmall pair:
+    conv: 2*Cout*27*Cin*Do*Ho*Wo ; transposed: 2*Cin*Cout*27*Di*Hi*Wi."""
+    h, w, d = 161, 513, MAX_DISP
+    f = 0.0
+    f += 2 * 32 * 27 * 64 * d * h * w + 2 * 32 * 27 * 32 * d * h * w                        # conv3D_1, 2
+    d2, h2, w2 = d // 2, 81, 257
+    f += 2 * 64 * 27 * 32 * d2 * h2 * w2 + 2 * (2 * 64 * 27 * 64 * d2 * h2 * w2)            # 3ds, 4, 5
+    d3, h3, w3 = d2 // 2, 41, 129
+    f += 2 * 128 * 27 * 64 * d3 * h3 * w3 + 2 * (2 * 128 * 27 * 128 * d3 * h3 * w3)         # 6ds, 7, 8
+    f += 2 * 128 * 64 * 27 * d3 * h3 * w3 + 2 * 64 * 32 * 27 * d2 * h2 * w2 + 2 * 32 * 1 * 27 * d * h * w   # deconv3D_1..3
+    return f
+
+
+COST_VOLUME_BYTES = (MAX_DISP * 64 * 161 * 513 + 2 * 32 * 161 * 513) * 4     # write + read, fp32 (1 036.0 MB)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return dict(hbm_gbs=j["hbm_gbs"], tflops_burst=j["bf16_tflops"], tflops_sustained=j.get("bf16_tflops_sustained", j["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU with NVML every 100 ms while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def cpu_baseline(max_seconds=60.0):
+    """The reference's algorithm on the host cores: the fixture-pinned PyTorch-CPU oracle (a port -- TensorFlow and
+    the reference's TensorRT build do not exist here), fp32, all cores, on a bounded sample of the same workload."""
+    import torch
+    from oracle import nets, io as oio
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wts = oio.read_weights(WEIGHTS)
+    l, r = synthetic_pairs(1)
+    # Calibrate on a thin band, then take the largest band of the 1025-wide workload that fits the time budget.
+    t0 = time.perf_counter()
+    nets.stereo_forward("nvsmall", wts, l[0][:, :33], r[0][:, :33])
+    t_band = time.perf_counter() - t0
+    rows = 321
+    est = t_band * 321 / 33
+    if est > max_seconds:
+        rows = max(33, int(321 * max_seconds / est) // 32 * 32 + 1)
+    t0 = time.perf_counter()
+    nets.stereo_forward("nvsmall", wts, l[0][:, :rows], r[0][:, :rows])
+    dt = time.perf_counter() - t0
+    frac = rows / 321.0
+    return {"value": frac / dt, "unit": "stereo pairs/s", "cores": cores, "kind": "port",
+            "sample": "1 NVSmall pass over a 1025x%d band (%.0f%% of a 1025x321 pair; cost is linear in rows), "
+                      "PyTorch-CPU fp32 oracle, %d threads, %.1f s" % (rows, 100 * frac, cores, dt)}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), timed on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import nets, io as oio
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wts = oio.read_weights(WEIGHTS)
+    l, r = synthetic_pairs(1)
+    t0 = time.perf_counter()
+    nets.stereo_forward("nvsmall", wts, l[0][:, :33], r[0][:, :33])
+    t_band = time.perf_counter() - t0
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    rows = 321 if t_band * 321 / 33 <= budget else max(33, int(321 * budget / (t_band * 321 / 33)) // 32 * 32 + 1)
+    for _ in range(args.warmup):
+        nets.stereo_forward("nvsmall", wts, l[0][:, :rows], r[0][:, :rows])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        nets.stereo_forward("nvsmall", wts, l[0][:, :rows], r[0][:, :rows])
+    dt = time.perf_counter() - t0
+    frac = rows / 321.0
+    value = frac * args.steps / dt
+    sample = "each step = 1 NVSmall pass over a 1025x%d band (%.0f%% of a pair), PyTorch-CPU fp32 oracle port, %d threads" % (rows, 100 * frac, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "stereo pairs/sec NVSmall 1025x321", "value": value, "unit": "stereo pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": value / PUBLISHED_PAIRS_PER_S, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": "NVSmall 1025x321 fp32 batch=1 (reference CPU path, oracle port)"},
+        "cpu_baseline": {"value": value, "unit": "stereo pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "stereo pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1, help="stereo pairs per GPU per step (BASELINE config: 1)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this engine has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from redtail_b200 import StereoEngine, ops
+    B = args.batch
+    eng = StereoEngine("nvsmall", H, W, WEIGHTS, max_batch=B)
+    left_np, right_np = synthetic_pairs(B, seed=1234 + 100 * rank)
+    h_left = torch.from_numpy(left_np).pin_memory()
+    h_right = torch.from_numpy(right_np).pin_memory()
+    h_disp = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+    d_left, d_right = h_left.cuda(), h_right.cuda()
+    d_disp = torch.empty((B, H, W), dtype=torch.float32, device="cuda")
+    gathered = torch.empty((world * B, H, W), dtype=torch.float32, device="cuda") if world > 1 else None
+
+    def step_device():
+        eng(d_left, d_right, out=d_disp)
+        if world > 1:      # the one exchange of the path: collect every rank's disparity maps (NCCL over NVLink)
+            dist.all_gather_into_tensor(gathered, d_disp)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) ----
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    launches = ops.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # ---- end to end through the public API with host buffers (`e2e`) ----
+    def step_host():
+        eng.execute_host(h_left, h_right, h_disp)      # H2D x2 + inference + D2H, synchronous
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, d_disp.copy_(h_disp, non_blocking=True))
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    sampler.stop_flag = True
+    sampler.join()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel roofline numbers: CUDA events around every engine step, on the engine's stream ----
+    peaks = measured_peaks()
+    prof_runs = 5
+    acc = {}
+    for _ in range(prof_runs):
+        for name, t_ms in eng.profile(d_left, d_right):
+            acc[name] = acc.get(name, 0.0) + t_ms / prof_runs
+    conv_ms = sum(t for n, t in acc.items() if n.startswith("conv3D_") or n.startswith("deconv3D_"))
+    n_conv = sum(1 for n in acc if n.startswith("conv3D_") or n.startswith("deconv3D_"))
+    cv_ms = sum(t for n, t in acc.items() if n.startswith("cost_vol"))
+    total_ms = sum(acc.values())
+    flops = conv_stack_flops() * B
+    achieved_tf = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved_tf / peaks["tflops_sustained"], "traffic": None,
+                "kernel": "3-D conv / transposed-conv stack (%d launches/step), algorithmic %.1f GFLOP/pair" % (n_conv, conv_stack_flops() / 1e9),
+                "peak_source": peaks["source"] + " cuBLAS bf16 (sustained)", "share_of_step": conv_ms / total_ms if total_ms else None,
+                "precision": os.environ.get("REDTAIL_CONV3D_PRECISION", "fp32") + " (" + ops.last_kernel() + ")"}
+    cv_gbs = COST_VOLUME_BYTES * B / (cv_ms * 1e-3) / 1e9 if cv_ms > 0 else 0.0
+    roofline_cv = {"bound": "hbm", "achieved": cv_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": cv_gbs / peaks["hbm_gbs"],
+                   "traffic": None, "kernel": "cost volume (dense [D,2C,H,W] fp32), algorithmic 1036.0 MB/pair",
+                   "peak_source": peaks["source"] + " copy", "share_of_step": cv_ms / total_ms if total_ms else None}
+
+    pairs = world * B * args.steps
+    value = pairs / (ms * 1e-3)
+    out = {
+        "metric": "stereo pairs/sec NVSmall 1025x321", "value": value, "unit": "stereo pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": value / PUBLISHED_PAIRS_PER_S,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "NVSmall 1025x321 fp32 batch=%d per GPU (BASELINE configs[1]): 2-D towers + cost volume D=48 + 11-layer 3-D conv stack + soft-argmin, reference's trained weights" % B,
+                   "pairs_per_step": world * B, "parallelism": "dp%d (independent pairs, NCCL all-gather of disparity maps)" % world,
+                   "l2": "per-step working set (1.0 GB cost volume + 0.5 GB activations per layer) >> 126 MB L2; no explicit flush",
+                   "vs_baseline_ref": "450 ms/pair TensorRT fp32 on Titan Xp (stereoDNN/README.md:28)"},
+        "e2e": {"value": pairs / e2e_s, "unit": "stereo pairs/s", "h2d_bytes_per_step": int(2 * B * 3 * H * W * 4),
+                "d2h_bytes_per_step": int(B * H * W * 4)},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": roofline,
+        "roofline_cost_volume": roofline_cv,
+        "layer_ms": {k: round(v, 4) for k, v in acc.items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

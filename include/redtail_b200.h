@@ -1,0 +1,128 @@
+/*
+ * redtail_b200.h -- the C-ABI of libredtail_b200.so: hand-written sm_100a kernels behind the
+ * redtail stereoDNN plugin path.  Plain pointers and sizes only; every pointer named x/y/left/
+ * right/out/workspace is DEVICE memory, every `stream` is a cudaStream_t passed as void*.
+ * All entry points are asynchronous on `stream` and return 0 on success, otherwise the
+ * cudaError_t value (or a negative rt_status for argument errors) -- the convention of the
+ * reference's `enqueue()` (stereoDNN/lib/ *_plugin.cpp: "return 0 / -1 / cudaError_t").
+ *
+ * Each group cites the reference interface it replaces (paths relative to stereoDNN/):
+ *
+ *   rt_cost_volume            CudaKernels::computeCostVolume      lib/internal_utils.h:78-97, lib/kernels.cu:136-161
+ *   rt_corr_cost_volume       CudaKernels::computeCorrCostVolume  lib/kernels.cu:252-287
+ *   rt_elu                    EluPlugin::enqueue                  lib/elu_plugin.cpp:123-135 (cudnnActivationForward)
+ *   rt_softargmax             SoftargmaxPlugin::enqueue           lib/softargmax_plugin.cpp:167-205 (5 cuDNN passes)
+ *   rt_pad_planes             PaddingPlugin::enqueue              lib/padding_plugin.cpp:79-94
+ *   rt_slice_planes           SlicePlugin::enqueue                lib/slice_plugin.cpp:80-92
+ *   rt_transpose01            TransformPlugin::enqueue            lib/transform_plugin.cpp:94-108 (cudnnTransformTensor)
+ *   rt_conv3d_*               Conv3DPlugin                        lib/conv3d_plugin.cpp:102-136,187-216 (cudnnConvolutionForward+AddTensor)
+ *                             Conv3DTransposePlugin               lib/conv3d_transpose_plugin.cpp:116-151,205-243 (cudnnConvolutionBackwardData
+ *                                                                 + CudaKernels::addDBiasTo3DConv lib/kernels.cu:310-334)
+ *   rt_conv2d_* rt_scale rt_eltwise_sum rt_concat_channels rt_sigmoid
+ *                             the TensorRT-native layers the generated builders call
+ *                             (sample_app/nvsmall_1025x321_net.cpp:36-53,350; resnet18_2D_513x257_net.cpp:613,722,766)
+ *   rt_convert                CudaKernels::fp32Tofp16 / fp16Tofp32 lib/kernels.cu:340-375
+ *
+ * There is no CPU fallback anywhere behind this header.
+ */
+#ifndef REDTAIL_B200_H
+#define REDTAIL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Data types; values follow nvinfer1::DataType (kFLOAT = 0, kHALF = 1). */
+enum { RT_F32 = 0, RT_F16 = 1 };
+
+/* Argument-error codes (CUDA errors are returned as their positive cudaError_t value). */
+enum { RT_OK = 0, RT_ERR_ARG = -1, RT_ERR_UNSUPPORTED = -2, RT_ERR_NO_DEVICE = -3 };
+
+/* Tensor-core numerics of the 3-D convolution path (see DESIGN.md "Numerics"):
+ *   RT_PREC_FP32   fp32-accurate: every operand split into two fp16 terms (hi + 2^-11 lo), three tcgen05
+ *                  kind::f16 products accumulated in fp32 TMEM -- holds the 1e-3 disparity tolerance.
+ *   RT_PREC_FP16   single fp16 product, fp32 accumulate -- the reference's fp16 configs (1e-2 tolerance).
+ *   RT_PREC_SIMT   plain fp32 FMA on CUDA cores (validation path, no tensor cores).                        */
+enum { RT_PREC_FP32 = 0, RT_PREC_FP16 = 1, RT_PREC_SIMT = 2 };
+
+const char* rt_version(void);
+/* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
+uint64_t rt_launch_count(void);
+/* Name of the last kernel variant launched per op family, for tests that assert the tensor-core path ran. */
+const char* rt_last_kernel(void);
+
+/* ---- cost volume ------------------------------------------------------------------------------------ */
+/* left,right [n,c,h,w] -> out [n,max_disp,2c,h,w]:  out[d,ch]=left[ch]; out[d,c+ch,y,x]=right[ch,y,x-d] | 0. */
+int rt_cost_volume(int dtype, const void* left, const void* right, void* out,
+                   int n, int c, int h, int w, int max_disp, void* stream);
+/* left,right [n,c,h,w] -> out [n,max_disp,h,w]:  out[d,y,x] = sum_ch left[ch,y,x]*right[ch,y,x-d] | 0 (fp32 accumulate). */
+int rt_corr_cost_volume(int dtype, const void* left, const void* right, void* out,
+                        int n, int c, int h, int w, int max_disp, void* stream);
+
+/* ---- element-wise / data movement ------------------------------------------------------------------- */
+int rt_elu(int dtype, const void* x, void* y, int64_t count, void* stream);            /* x>0 ? x : expm1(x) */
+int rt_sigmoid(int dtype, const void* x, void* y, int64_t count, void* stream);
+int rt_scale(int dtype, const void* x, void* y, int64_t count, float shift, float scale, float power, void* stream);
+int rt_eltwise_sum(int dtype, const void* a, const void* b, void* y, int64_t count, void* stream);
+int rt_convert(int src_dtype, const void* x, int dst_dtype, void* y, int64_t count, void* stream);
+/* x [n, planes, plane_elems] -> y [n, planes+pad_end, plane_elems], appended planes zero. */
+int rt_pad_planes(int dtype, const void* x, void* y, int n, int planes, int64_t plane_elems, int pad_end, void* stream);
+/* x [n, planes, plane_elems] -> y [n, end-start, plane_elems]. */
+int rt_slice_planes(int dtype, const void* x, void* y, int n, int planes, int64_t plane_elems, int start, int end, void* stream);
+/* x [n, d0, d1, inner] -> y [n, d1, d0, inner]   (Transform{1,0,2,3}). */
+int rt_transpose01(int dtype, const void* x, void* y, int n, int d0, int d1, int64_t inner, void* stream);
+/* Channel concatenation of two [n,c_i,inner] tensors. */
+int rt_concat_channels(int dtype, const void* a, int ca, const void* b, int cb, void* y, int n, int64_t inner, void* stream);
+
+/* ---- soft-argmax ------------------------------------------------------------------------------------ */
+/* x [n,d,h*w] -> y [n,h*w]:  sum_d d*softmax_d(is_min ? -x : x), max-subtracted, fp32 math. */
+int rt_softargmax(int dtype, int is_min, const void* x, void* y, int n, int d, int64_t hw, void* stream);
+
+/* ---- 3-D convolution / transposed convolution plans -------------------------------------------------- */
+typedef struct rt_conv3d_plan rt_conv3d_plan;
+
+typedef struct {
+    int transposed;          /* 0: Conv3DPlugin, 1: Conv3DTransposePlugin                                    */
+    int k, v, c, r, s;       /* weight dims, KVCRS order (conv: K outputs/C inputs; transposed: K inputs/C outputs) */
+    int stride[3];           /* D,H,W                                                                        */
+    int pad[3];              /* symmetric pad (= the plugin's pad_start), D,H,W                               */
+    int in_dims[4];          /* conv: [D,C,H,W]   transposed: [K,D,H,W]                                       */
+    int out_dims[4];         /* conv: [K,Do,Ho,Wo] transposed: [Dx,C,Hx,Wx] (caller-supplied, as the plugin's) */
+    int weights_dtype;       /* RT_F32 | RT_F16 (host arrays)                                                */
+    const void* weights;     /* host, k*v*c*r*s elements                                                     */
+    const void* bias;        /* host, K (conv) or C (transposed) elements, or NULL                           */
+    int precision;           /* RT_PREC_*                                                                    */
+    int fuse_elu;            /* apply ELU in the epilogue                                                    */
+    int out_transposed;      /* conv only: write [Do,K,Ho,Wo] instead of [K,Do,Ho,Wo] (fuses Transform{1,0,2,3}) */
+    int slice_d;             /* transposed only: drop this many trailing D planes of out_dims (fuses SlicePlugin) */
+} rt_conv3d_desc;
+
+int  rt_conv3d_create(const rt_conv3d_desc* desc, rt_conv3d_plan** plan);   /* repacks + uploads weights        */
+void rt_conv3d_destroy(rt_conv3d_plan* plan);
+size_t rt_conv3d_workspace_size(const rt_conv3d_plan* plan, int max_batch);
+/* x, y dense fp32 in the layouts of rt_conv3d_desc; `skip` (may be NULL) is added before ELU, same layout as y. */
+int  rt_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const void* x, const void* skip, void* y,
+                       void* workspace, void* stream);
+
+/* ---- 2-D convolution / deconvolution (TensorRT-native layers of the builders) ------------------------ */
+typedef struct rt_conv2d_plan rt_conv2d_plan;
+typedef struct {
+    int transposed;          /* 0: IConvolutionLayer (weights KCRS), 1: IDeconvolutionLayer (weights [Cin,Cout,R,S]) */
+    int cin, cout, r, s;
+    int stride[2], pad[2];
+    int in_h, in_w;
+    int weights_dtype; const void* weights; const void* bias;   /* host */
+    int fuse_elu;
+} rt_conv2d_desc;
+int  rt_conv2d_create(const rt_conv2d_desc* desc, rt_conv2d_plan** plan);
+void rt_conv2d_destroy(rt_conv2d_plan* plan);
+void rt_conv2d_out_dims(const rt_conv2d_plan* plan, int* out_h, int* out_w);
+int  rt_conv2d_enqueue(const rt_conv2d_plan* plan, int n, const void* x, void* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REDTAIL_B200_H */

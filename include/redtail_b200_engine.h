@@ -1,0 +1,46 @@
+/*
+ * redtail_b200_engine.h -- C-ABI over the whole stereo network (libnvstereo_inference.so).
+ *
+ * What a host application of the reference does by hand in C++ -- read the weight file, call the generated
+ * create<Net>Network() builder, buildCudaEngine(), cudaMemcpy in, IExecutionContext::execute(), cudaMemcpy out
+ * (stereoDNN/sample_app/main.cpp:176-315; ros/packages/stereo_dnn_ros/src/stereo_dnn_ros_node.cpp:60-103,297-335) --
+ * exposed as plain C entry points so that Python (ctypes), bench.py and non-C++ hosts can drive it.  The engine behind
+ * it is the same nvinfer1-compatible engine the unchanged reference builders use; the network wiring comes from
+ * redtail_b200/csrc/host/nets.cpp, which goes through the same IPluginContainer / add* API.
+ */
+#ifndef REDTAIL_B200_ENGINE_H
+#define REDTAIL_B200_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rt_stereo_engine rt_stereo_engine;
+
+/* model: "nvsmall" (towers -> concat cost volume D -> 8 conv3d -> 3 transposed conv3d -> soft-argmin; covers the
+ *        reference's NVSmall 1025x321 [max_disp 48] and NVTiny 513x161 [max_disp 24] weight sets).
+ * weights_path: the reference's weight-file format (cstring name, u32 count, count x f32|f16).
+ * weights_dtype: RT_F32 | RT_F16.  Returns 0 or a negative rt_status / positive cudaError_t. */
+int rt_stereo_create(const char* model, int height, int width, int max_disp, const char* weights_path,
+                     int weights_dtype, int max_batch, rt_stereo_engine** engine);
+void rt_stereo_destroy(rt_stereo_engine* engine);
+
+/* Device buffers: left,right [batch,3,H,W] fp32, disp [batch,H,W] fp32.  Asynchronous on `stream` (cudaStream_t). */
+int rt_stereo_enqueue(rt_stereo_engine* engine, int batch, const float* left, const float* right, float* disp, void* stream);
+/* Host buffers (pinned for full speed): H2D copies, inference and the D2H copy, synchronous. */
+int rt_stereo_execute_host(rt_stereo_engine* engine, int batch, const float* left, const float* right, float* disp);
+/* Runs once with per-layer CUDA-event timing (IProfiler) and writes "layer name\tms\n" lines into buf. */
+int rt_stereo_profile(rt_stereo_engine* engine, int batch, const float* left, const float* right, float* disp,
+                      char* buf, size_t buf_len);
+/* Introspection. */
+int rt_stereo_num_layers(const rt_stereo_engine* engine);
+size_t rt_stereo_device_bytes(const rt_stereo_engine* engine);
+const char* rt_stereo_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

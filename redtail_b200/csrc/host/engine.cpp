@@ -1,0 +1,896 @@
+// Mini inference engine behind include/NvInfer.h: graph capture (INetworkDefinition), build (shape resolution,
+// plugin protocol, peephole fusion, static memory plan) and execution (one stream, optional per-layer profiling).
+//
+// It plays the role TensorRT plays for the reference (SURVEY.md layer L3): the generated builders call
+// network->add*(), buildCudaEngine() walks the layers in insertion order, and execute() runs them -- every step is a
+// call into the C-ABI of include/redtail_b200.h (native layers) or a plugin's enqueue().
+//
+// Fusion (REDTAIL_ENGINE_FUSION=0 disables it; the unfused graph is what the reference's TensorRT would run):
+//   Conv2D/Deconv2D -> ELU                                  => one conv2d launch with ELU epilogue
+//   Conv3D [-> Transform{1,0,2,3}] [-> ELU]                 => one conv3d launch (layout + ELU in the epilogue)
+//   Conv3DTranspose [-> Slice] [-> +skip (kSUM)] [-> ELU]   => one transposed-conv launch
+// Intermediate tensors of a fused chain are never materialised.
+#include <cuda_runtime_api.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "internal_utils.h"
+#include "op_info.h"
+#include "redtail_b200.h"
+
+using namespace nvinfer1;
+using redtail::tensorrt::DimsUtils;
+using redtail::tensorrt::IRedtailOp;
+using redtail::tensorrt::OpInfo;
+using redtail::tensorrt::OpKind;
+
+namespace {
+
+int rtType(DataType t) { return t == DataType::kHALF ? RT_F16 : RT_F32; }
+
+size_t volume(const Dims& d) { return DimsUtils::getTensorSize(d); }
+
+void logMsg(ILogger& log, ILogger::Severity sev, const std::string& s) { log.log(sev, s.c_str()); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Network definition
+// ------------------------------------------------------------------------------------------------------------------
+class NetworkImpl;
+
+struct TensorImpl : public ITensor {
+    NetworkImpl* net = nullptr;
+    int id = -1;
+    std::string name;
+    Dims dims{};
+    DataType type = DataType::kFLOAT;
+    bool is_input = false, is_output = false;
+    int producer = -1;      // layer index, -1 for network inputs
+
+    void setName(const char* n) override { name = n ? n : ""; }
+    const char* getName() const override { return name.c_str(); }
+    Dims getDimensions() const override;
+    DataType getType() const override { return type; }
+    bool isNetworkInput() const override { return is_input; }
+    bool isNetworkOutput() const override { return is_output; }
+};
+
+enum class LKind { kConv, kDeconv, kScale, kEltwise, kConcat, kActivation, kShuffle, kPlugin };
+
+struct LayerData {
+    LKind kind;
+    LayerType type;
+    std::string name;
+    std::vector<TensorImpl*> in, out;
+    int nb_out_maps = 0;
+    DimsHW ksize{1, 1}, stride{1, 1}, pad{0, 0};
+    Weights kw{DataType::kFLOAT, nullptr, 0}, bw{DataType::kFLOAT, nullptr, 0};
+    ScaleMode smode = ScaleMode::kUNIFORM;
+    Weights shift{DataType::kFLOAT, nullptr, 0}, scale{DataType::kFLOAT, nullptr, 0}, power{DataType::kFLOAT, nullptr, 0};
+    ElementWiseOperation eop = ElementWiseOperation::kSUM;
+    ActivationType act = ActivationType::kRELU;
+    Dims reshape{};
+    bool has_reshape = false;
+    IPlugin* plugin = nullptr;
+    IPluginExt* plugin_ext = nullptr;
+};
+
+struct LayerNode {
+    virtual ~LayerNode() {}
+    LayerData d;
+    virtual ILayer* iface() = 0;
+};
+
+template <class Iface>
+struct LayerT : public Iface, public LayerNode {
+    ILayer* iface() override { return this; }
+    LayerType getType() const override { return d.type; }
+    void setName(const char* n) override { d.name = n ? n : ""; }
+    const char* getName() const override { return d.name.c_str(); }
+    int getNbInputs() const override { return static_cast<int>(d.in.size()); }
+    ITensor* getInput(int i) const override { return i >= 0 && i < getNbInputs() ? d.in[i] : nullptr; }
+    int getNbOutputs() const override { return static_cast<int>(d.out.size()); }
+    ITensor* getOutput(int i) const override { return i >= 0 && i < getNbOutputs() ? d.out[i] : nullptr; }
+};
+
+template <class Iface>
+struct ConvLikeLayer : public LayerT<Iface> {
+    void setKernelSize(DimsHW k) override { this->d.ksize = k; }
+    DimsHW getKernelSize() const override { return this->d.ksize; }
+    void setNbOutputMaps(int n) override { this->d.nb_out_maps = n; }
+    int getNbOutputMaps() const override { return this->d.nb_out_maps; }
+    void setStride(DimsHW s) override { this->d.stride = s; }
+    DimsHW getStride() const override { return this->d.stride; }
+    void setPadding(DimsHW p) override { this->d.pad = p; }
+    DimsHW getPadding() const override { return this->d.pad; }
+    void setKernelWeights(Weights w) override { this->d.kw = w; }
+    Weights getKernelWeights() const override { return this->d.kw; }
+    void setBiasWeights(Weights w) override { this->d.bw = w; }
+    Weights getBiasWeights() const override { return this->d.bw; }
+};
+using ConvLayer = ConvLikeLayer<IConvolutionLayer>;
+using DeconvLayer = ConvLikeLayer<IDeconvolutionLayer>;
+struct ScaleLayer : public LayerT<IScaleLayer> { ScaleMode getMode() const override { return d.smode; } };
+struct EltwiseLayer : public LayerT<IElementWiseLayer> { ElementWiseOperation getOperation() const override { return d.eop; } };
+struct ConcatLayer : public LayerT<IConcatenationLayer> {};
+struct ActivationLayer : public LayerT<IActivationLayer> { ActivationType getActivationType() const override { return d.act; } };
+struct ShuffleLayer : public LayerT<IShuffleLayer> {
+    void setReshapeDimensions(Dims dims) override { d.reshape = dims; d.has_reshape = true; }
+    Dims getReshapeDimensions() const override { return d.reshape; }
+};
+struct PluginLayer : public LayerT<IPluginLayer> { IPlugin& getPlugin() override { return *d.plugin; } };
+
+class NetworkImpl : public INetworkDefinition {
+public:
+    explicit NetworkImpl(ILogger& log) : log_(log) {}
+    ~NetworkImpl() override {}
+
+    ITensor* addInput(const char* name, DataType type, Dims dims) override
+    {
+        if (dims.nbDims < 1 || dims.nbDims > 4) { logMsg(log_, ILogger::Severity::kERROR, "addInput: rank must be 1..4"); return nullptr; }
+        TensorImpl* t = newTensor(name ? name : "");
+        t->type = type; t->dims = dims; t->is_input = true;
+        inputs_.push_back(t);
+        return t;
+    }
+    void markOutput(ITensor& tensor) override
+    {
+        TensorImpl* t = static_cast<TensorImpl*>(&tensor);
+        t->is_output = true;
+        outputs_.push_back(t);
+    }
+    IConvolutionLayer* addConvolution(ITensor& input, int nbOutputMaps, DimsHW kernelSize, Weights kw, Weights bw) override
+    {
+        auto* l = add<ConvLayer>(LKind::kConv, LayerType::kCONVOLUTION, {&input}, 1);
+        l->d.nb_out_maps = nbOutputMaps; l->d.ksize = kernelSize; l->d.kw = kw; l->d.bw = bw;
+        return l;
+    }
+    IDeconvolutionLayer* addDeconvolution(ITensor& input, int nbOutputMaps, DimsHW kernelSize, Weights kw, Weights bw) override
+    {
+        auto* l = add<DeconvLayer>(LKind::kDeconv, LayerType::kDECONVOLUTION, {&input}, 1);
+        l->d.nb_out_maps = nbOutputMaps; l->d.ksize = kernelSize; l->d.kw = kw; l->d.bw = bw;
+        return l;
+    }
+    IActivationLayer* addActivation(ITensor& input, ActivationType type) override
+    {
+        auto* l = add<ActivationLayer>(LKind::kActivation, LayerType::kACTIVATION, {&input}, 1);
+        l->d.act = type;
+        return l;
+    }
+    IScaleLayer* addScale(ITensor& input, ScaleMode mode, Weights shift, Weights scale, Weights power) override
+    {
+        auto* l = add<ScaleLayer>(LKind::kScale, LayerType::kSCALE, {&input}, 1);
+        l->d.smode = mode; l->d.shift = shift; l->d.scale = scale; l->d.power = power;
+        return l;
+    }
+    IConcatenationLayer* addConcatenation(ITensor* const* inputs, int nbInputs) override
+    {
+        std::vector<ITensor*> in(inputs, inputs + nbInputs);
+        return add<ConcatLayer>(LKind::kConcat, LayerType::kCONCATENATION, in, 1);
+    }
+    IElementWiseLayer* addElementWise(ITensor& a, ITensor& b, ElementWiseOperation op) override
+    {
+        auto* l = add<EltwiseLayer>(LKind::kEltwise, LayerType::kELEMENTWISE, {&a, &b}, 1);
+        l->d.eop = op;
+        return l;
+    }
+    IShuffleLayer* addShuffle(ITensor& input) override
+    {
+        return add<ShuffleLayer>(LKind::kShuffle, LayerType::kSHUFFLE, {&input}, 1);
+    }
+    IPluginLayer* addPlugin(ITensor* const* inputs, int nbInputs, IPlugin& plugin) override
+    {
+        std::vector<ITensor*> in(inputs, inputs + nbInputs);
+        auto* l = add<PluginLayer>(LKind::kPlugin, LayerType::kPLUGIN, in, plugin.getNbOutputs());
+        l->d.plugin = &plugin;
+        return l;
+    }
+    IPluginLayer* addPluginExt(ITensor* const* inputs, int nbInputs, IPluginExt& plugin) override
+    {
+        std::vector<ITensor*> in(inputs, inputs + nbInputs);
+        auto* l = add<PluginLayer>(LKind::kPlugin, LayerType::kPLUGIN, in, plugin.getNbOutputs());
+        l->d.plugin = &plugin; l->d.plugin_ext = &plugin;
+        return l;
+    }
+    int getNbLayers() const override { return static_cast<int>(layers_.size()); }
+    ILayer* getLayer(int i) const override { return i >= 0 && i < getNbLayers() ? layers_[i]->iface() : nullptr; }
+    int getNbInputs() const override { return static_cast<int>(inputs_.size()); }
+    ITensor* getInput(int i) const override { return i >= 0 && i < getNbInputs() ? inputs_[i] : nullptr; }
+    int getNbOutputs() const override { return static_cast<int>(outputs_.size()); }
+    ITensor* getOutput(int i) const override { return i >= 0 && i < getNbOutputs() ? outputs_[i] : nullptr; }
+    void destroy() override { delete this; }
+
+    // Computes the dims of every tensor not yet resolved (layers are in topological = insertion order).
+    bool resolve()
+    {
+        for (size_t li = resolved_; li < layers_.size(); ++li) {
+            if (!resolveLayer(layers_[li]->d)) return false;
+        }
+        resolved_ = layers_.size();
+        return true;
+    }
+    // A layer's parameters (stride / padding / reshape) may be set after add*(): force re-resolution before build.
+    void invalidate() { resolved_ = 0; }
+
+    ILogger& log_;
+    std::vector<std::unique_ptr<TensorImpl>> tensors_;
+    std::vector<std::unique_ptr<LayerNode>> layers_;
+    std::vector<TensorImpl*> inputs_, outputs_;
+
+private:
+    TensorImpl* newTensor(const std::string& name)
+    {
+        tensors_.emplace_back(new TensorImpl());
+        TensorImpl* t = tensors_.back().get();
+        t->net = this; t->id = static_cast<int>(tensors_.size()) - 1; t->name = name;
+        return t;
+    }
+    template <class L>
+    L* add(LKind kind, LayerType type, std::vector<ITensor*> in, int nb_out)
+    {
+        L* l = new L();
+        layers_.emplace_back(l);
+        l->d.kind = kind; l->d.type = type;
+        l->d.name = "(Unnamed Layer* " + std::to_string(layers_.size() - 1) + ")";
+        for (ITensor* t : in) l->d.in.push_back(static_cast<TensorImpl*>(t));
+        for (int i = 0; i < nb_out; ++i) {
+            TensorImpl* t = newTensor(l->d.name + "_output_" + std::to_string(i));
+            t->producer = static_cast<int>(layers_.size()) - 1;
+            l->d.out.push_back(t);
+        }
+        return l;
+    }
+    bool fail(const LayerData& d, const std::string& why)
+    {
+        logMsg(log_, ILogger::Severity::kERROR, d.name + ": " + why);
+        return false;
+    }
+    bool resolveLayer(LayerData& d)
+    {
+        for (auto* t : d.in)
+            if (t == nullptr) return fail(d, "null input tensor");
+        const Dims in0 = d.in[0]->dims;
+        switch (d.kind) {
+            case LKind::kConv:
+            case LKind::kDeconv: {
+                if (in0.nbDims != 3) return fail(d, "2-D convolution expects a CHW input");
+                const int cin = in0.d[0];
+                if (d.kw.count != static_cast<int64_t>(cin) * d.nb_out_maps * d.ksize.h() * d.ksize.w())
+                    return fail(d, "kernel weight count does not match the layer shape");
+                if (d.bw.count != 0 && d.bw.count != d.nb_out_maps) return fail(d, "bias count mismatch");
+                int ho, wo;
+                if (d.kind == LKind::kConv) {
+                    ho = (in0.d[1] + 2 * d.pad.h() - d.ksize.h()) / d.stride.h() + 1;
+                    wo = (in0.d[2] + 2 * d.pad.w() - d.ksize.w()) / d.stride.w() + 1;
+                } else {
+                    ho = (in0.d[1] - 1) * d.stride.h() + d.ksize.h() - 2 * d.pad.h();
+                    wo = (in0.d[2] - 1) * d.stride.w() + d.ksize.w() - 2 * d.pad.w();
+                }
+                if (ho <= 0 || wo <= 0) return fail(d, "empty output");
+                d.out[0]->dims = DimsCHW(d.nb_out_maps, ho, wo);
+                break;
+            }
+            case LKind::kScale:
+                if (d.smode != ScaleMode::kUNIFORM) return fail(d, "only ScaleMode::kUNIFORM is supported");
+                d.out[0]->dims = in0;
+                break;
+            case LKind::kActivation:
+                d.out[0]->dims = in0;
+                break;
+            case LKind::kEltwise:
+                if (d.eop != ElementWiseOperation::kSUM) return fail(d, "only ElementWiseOperation::kSUM is supported");
+                if (!DimsUtils::areEqual(in0, d.in[1]->dims)) return fail(d, "element-wise inputs differ in shape");
+                d.out[0]->dims = in0;
+                break;
+            case LKind::kConcat: {
+                Dims o = in0;
+                if (o.nbDims != 3) return fail(d, "concatenation expects CHW inputs");
+                for (size_t i = 1; i < d.in.size(); ++i) {
+                    const Dims& di = d.in[i]->dims;
+                    if (di.nbDims != 3 || di.d[1] != o.d[1] || di.d[2] != o.d[2]) return fail(d, "concat inputs differ in H/W");
+                    o.d[0] += di.d[0];
+                }
+                d.out[0]->dims = o;
+                break;
+            }
+            case LKind::kShuffle: {
+                Dims o = d.has_reshape ? d.reshape : in0;
+                if (volume(o) != volume(in0)) return fail(d, "reshape changes the element count");
+                d.out[0]->dims = o;
+                break;
+            }
+            case LKind::kPlugin: {
+                std::vector<Dims> ind;
+                for (auto* t : d.in) ind.push_back(t->dims);
+                for (size_t i = 0; i < d.out.size(); ++i)
+                    d.out[i]->dims = d.plugin->getOutputDimensions(static_cast<int>(i), ind.data(), static_cast<int>(ind.size()));
+                break;
+            }
+        }
+        return true;
+    }
+    size_t resolved_ = 0;
+};
+
+Dims TensorImpl::getDimensions() const
+{
+    if (net) net->resolve();
+    return dims;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Engine
+// ------------------------------------------------------------------------------------------------------------------
+struct TensorSlot {
+    std::string name;
+    Dims dims{};
+    size_t elems = 0;          // per sample
+    int binding = -1;          // >= 0: caller-owned buffer
+    int alias_of = -1;         // shares storage with another tensor (shuffle)
+    size_t offset = 0;         // arena offset (bytes) when neither binding nor alias
+    int first = -1, last = -1; // step liveness
+    bool used = false;
+};
+
+struct Step {
+    std::string name;
+    std::vector<int> in, out;  // tensor ids (for liveness)
+    size_t workspace = 0;
+    // ptr(id) resolves a tensor id to its device pointer for this execution.
+    std::function<int(int batch, const std::function<void*(int)>& ptr, void* workspace, cudaStream_t)> run;
+};
+
+class EngineImpl;
+
+class ContextImpl : public IExecutionContext {
+public:
+    explicit ContextImpl(EngineImpl* e) : engine_(e) { cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking); }
+    ~ContextImpl() override { if (stream_) cudaStreamDestroy(stream_); }
+    bool execute(int batchSize, void** bindings) override;
+    bool enqueue(int batchSize, void** bindings, cudaStream_t stream, cudaEvent_t* inputConsumed) override;
+    void setDebugSync(bool sync) override { debug_sync_ = sync; }
+    bool getDebugSync() const override { return debug_sync_; }
+    void setProfiler(IProfiler* p) override { profiler_ = p; }
+    IProfiler* getProfiler() const override { return profiler_; }
+    const ICudaEngine& getEngine() const override;
+    void destroy() override { delete this; }
+
+private:
+    bool run(int batchSize, void** bindings, cudaStream_t stream, bool profile);
+    EngineImpl* engine_;
+    cudaStream_t stream_ = nullptr;
+    IProfiler* profiler_ = nullptr;
+    bool debug_sync_ = false;
+};
+
+class EngineImpl : public ICudaEngine {
+public:
+    EngineImpl(ILogger& log) : log_(log) {}
+    ~EngineImpl() override
+    {
+        for (auto* p : configured_plugins_) p->terminate();
+        for (auto* p : conv2d_plans_) rt_conv2d_destroy(p);
+        for (auto* p : conv3d_plans_) rt_conv3d_destroy(p);
+        if (arena_) cudaFree(arena_);
+        if (workspace_) cudaFree(workspace_);
+    }
+    int getNbBindings() const override { return static_cast<int>(bindings_.size()); }
+    int getBindingIndex(const char* name) const override
+    {
+        for (size_t i = 0; i < bindings_.size(); ++i)
+            if (slots_[bindings_[i]].name == name) return static_cast<int>(i);
+        return -1;
+    }
+    const char* getBindingName(int i) const override { return i >= 0 && i < getNbBindings() ? slots_[bindings_[i]].name.c_str() : nullptr; }
+    bool bindingIsInput(int i) const override { return i >= 0 && i < nb_inputs_; }
+    Dims getBindingDimensions(int i) const override { return i >= 0 && i < getNbBindings() ? slots_[bindings_[i]].dims : Dims{}; }
+    DataType getBindingDataType(int) const override { return DataType::kFLOAT; }
+    int getMaxBatchSize() const override { return max_batch_; }
+    int getNbLayers() const override { return static_cast<int>(steps_.size()); }
+    size_t getWorkspaceSize() const override { return workspace_bytes_; }
+    IHostMemory* serialize() const override
+    {
+        logMsg(log_, ILogger::Severity::kERROR, "ICudaEngine::serialize: engine plans are not serialisable in this build.");
+        return nullptr;
+    }
+    IExecutionContext* createExecutionContext() override { return new ContextImpl(this); }
+    void destroy() override { delete this; }
+
+    bool build(NetworkImpl& net, int max_batch, bool half2);
+
+    ILogger& log_;
+    int max_batch_ = 1;
+    int nb_inputs_ = 0;
+    std::vector<TensorSlot> slots_;
+    std::vector<int> bindings_;          // binding index -> tensor id
+    std::vector<Step> steps_;
+    void* arena_ = nullptr;
+    size_t arena_bytes_ = 0;
+    void* workspace_ = nullptr;
+    size_t workspace_bytes_ = 0;
+    std::vector<IPlugin*> configured_plugins_;
+    std::vector<rt_conv2d_plan*> conv2d_plans_;
+    std::vector<rt_conv3d_plan*> conv3d_plans_;
+
+private:
+    bool fail(const std::string& s) { logMsg(log_, ILogger::Severity::kERROR, s); return false; }
+    bool planMemory();
+};
+
+const ICudaEngine& ContextImpl::getEngine() const { return *engine_; }
+
+// Weight helpers ---------------------------------------------------------------------------------------------------
+float weightScalar(const Weights& w, float dflt)
+{
+    if (w.count < 1 || w.values == nullptr) return dflt;
+    if (w.type == DataType::kFLOAT) return *static_cast<const float*>(w.values);
+    // fp16 scalar
+    const uint16_t h = *static_cast<const uint16_t*>(w.values);
+    const uint32_t sign = (h & 0x8000u) << 16, exp = (h >> 10) & 0x1F, man = h & 0x3FF;
+    uint32_t bits;
+    if (exp == 0) bits = sign;        // zero / subnormal scalars are not meaningful for scale layers
+    else if (exp == 31) bits = sign | 0x7F800000u | (man << 13);
+    else bits = sign | ((exp + 112) << 23) | (man << 13);
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+
+bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
+{
+    max_batch_ = max_batch > 0 ? max_batch : 1;
+    net.invalidate();
+    if (!net.resolve()) return false;
+    if (net.outputs_.empty()) return fail("network has no outputs");
+
+    static const bool fusion = [] { const char* e = getenv("REDTAIL_ENGINE_FUSION"); return !(e && e[0] == '0'); }();
+
+    // Tensor table.
+    slots_.resize(net.tensors_.size());
+    for (size_t i = 0; i < net.tensors_.size(); ++i) {
+        const TensorImpl& t = *net.tensors_[i];
+        slots_[i].name = t.name; slots_[i].dims = t.dims; slots_[i].elems = volume(t.dims);
+    }
+    for (auto* t : net.inputs_) { slots_[t->id].binding = static_cast<int>(bindings_.size()); bindings_.push_back(t->id); }
+    nb_inputs_ = static_cast<int>(bindings_.size());
+    for (auto* t : net.outputs_) {
+        if (slots_[t->id].binding >= 0) return fail("tensor '" + t->name + "' bound twice");
+        slots_[t->id].binding = static_cast<int>(bindings_.size()); bindings_.push_back(t->id);
+    }
+
+    // Consumer counts (for fusion legality).
+    const int nl = static_cast<int>(net.layers_.size());
+    std::vector<int> consumers(net.tensors_.size(), 0);
+    std::vector<std::vector<int>> consumer_layers(net.tensors_.size());
+    for (int li = 0; li < nl; ++li)
+        for (auto* t : net.layers_[li]->d.in) { consumers[t->id]++; consumer_layers[t->id].push_back(li); }
+    auto soleConsumer = [&](TensorImpl* t) -> int {   // layer index, or -1
+        if (t->is_output || consumers[t->id] != 1) return -1;
+        return consumer_layers[t->id][0];
+    };
+    auto opOf = [&](int li) -> const OpInfo* {
+        const LayerData& d = net.layers_[li]->d;
+        if (d.kind != LKind::kPlugin) return nullptr;
+        auto* op = dynamic_cast<IRedtailOp*>(d.plugin);
+        return op ? &op->opInfo() : nullptr;
+    };
+    auto isFp32Elu = [&](int li) {
+        const OpInfo* o = li >= 0 ? opOf(li) : nullptr;
+        return o && o->kind == OpKind::kElu && o->data_type == DataType::kFLOAT;
+    };
+
+    std::vector<bool> done(nl, false);
+    for (int li = 0; li < nl; ++li) {
+        if (done[li]) continue;
+        LayerData& d = net.layers_[li]->d;
+        done[li] = true;
+        Step st;
+        st.name = d.name;
+        for (auto* t : d.in) st.in.push_back(t->id);
+        switch (d.kind) {
+            case LKind::kConv:
+            case LKind::kDeconv: {
+                rt_conv2d_desc cd{};
+                cd.transposed = d.kind == LKind::kDeconv;
+                cd.cin = d.in[0]->dims.d[0]; cd.cout = d.nb_out_maps;
+                cd.r = d.ksize.h(); cd.s = d.ksize.w();
+                cd.stride[0] = d.stride.h(); cd.stride[1] = d.stride.w();
+                cd.pad[0] = d.pad.h(); cd.pad[1] = d.pad.w();
+                cd.in_h = d.in[0]->dims.d[1]; cd.in_w = d.in[0]->dims.d[2];
+                cd.weights_dtype = rtType(d.kw.type); cd.weights = d.kw.values;
+                cd.bias = d.bw.count > 0 ? d.bw.values : nullptr;
+                TensorImpl* out = d.out[0];
+                const int nxt = fusion ? soleConsumer(out) : -1;
+                if (isFp32Elu(nxt)) {
+                    cd.fuse_elu = 1;
+                    done[nxt] = true;
+                    out = net.layers_[nxt]->d.out[0];
+                    st.name += " + " + net.layers_[nxt]->d.name;
+                }
+                rt_conv2d_plan* plan = nullptr;
+                const int rc = rt_conv2d_create(&cd, &plan);
+                if (rc != RT_OK) return fail(d.name + ": rt_conv2d_create failed (" + std::to_string(rc) + ")");
+                conv2d_plans_.push_back(plan);
+                const int in_id = d.in[0]->id, out_id = out->id;
+                st.out.push_back(out_id);
+                st.run = [plan, in_id, out_id](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                    return rt_conv2d_enqueue(plan, batch, ptr(in_id), ptr(out_id), s);
+                };
+                break;
+            }
+            case LKind::kScale: {
+                const float shift = weightScalar(d.shift, 0.f), scale = weightScalar(d.scale, 1.f), power = weightScalar(d.power, 1.f);
+                const int in_id = d.in[0]->id, out_id = d.out[0]->id;
+                const int64_t elems = static_cast<int64_t>(slots_[in_id].elems);
+                st.out.push_back(out_id);
+                st.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                    return rt_scale(RT_F32, ptr(in_id), ptr(out_id), elems * batch, shift, scale, power, s);
+                };
+                break;
+            }
+            case LKind::kActivation: {
+                if (d.act != ActivationType::kSIGMOID) return fail(d.name + ": only ActivationType::kSIGMOID is supported");
+                const int in_id = d.in[0]->id, out_id = d.out[0]->id;
+                const int64_t elems = static_cast<int64_t>(slots_[in_id].elems);
+                st.out.push_back(out_id);
+                st.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                    return rt_sigmoid(RT_F32, ptr(in_id), ptr(out_id), elems * batch, s);
+                };
+                break;
+            }
+            case LKind::kEltwise: {
+                const int a = d.in[0]->id, b = d.in[1]->id, out_id = d.out[0]->id;
+                const int64_t elems = static_cast<int64_t>(slots_[a].elems);
+                st.out.push_back(out_id);
+                st.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                    return rt_eltwise_sum(RT_F32, ptr(a), ptr(b), ptr(out_id), elems * batch, s);
+                };
+                break;
+            }
+            case LKind::kConcat: {
+                if (d.in.size() != 2) return fail(d.name + ": concatenation of exactly two tensors is supported");
+                const int a = d.in[0]->id, b = d.in[1]->id, out_id = d.out[0]->id;
+                const int ca = d.in[0]->dims.d[0], cb = d.in[1]->dims.d[0];
+                const int64_t inner = static_cast<int64_t>(d.in[0]->dims.d[1]) * d.in[0]->dims.d[2];
+                st.out.push_back(out_id);
+                st.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                    return rt_concat_channels(RT_F32, ptr(a), ca, ptr(b), cb, ptr(out_id), batch, inner, s);
+                };
+                break;
+            }
+            case LKind::kShuffle: {
+                const int in_id = d.in[0]->id, out_id = d.out[0]->id;
+                if (slots_[out_id].binding < 0) {          // pure reshape: alias, no step
+                    slots_[out_id].alias_of = in_id;
+                    continue;
+                }
+                const int64_t elems = static_cast<int64_t>(slots_[in_id].elems);
+                st.out.push_back(out_id);
+                st.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                    return static_cast<int>(cudaMemcpyAsync(ptr(out_id), ptr(in_id), elems * batch * sizeof(float), cudaMemcpyDeviceToDevice, s));
+                };
+                break;
+            }
+            case LKind::kPlugin: {
+                const OpInfo* op = opOf(li);
+                // ---- fused 3-D convolution chains --------------------------------------------------------------
+                if (fusion && op && (op->kind == OpKind::kConv3D || op->kind == OpKind::kConv3DTranspose)) {
+                    rt_conv3d_desc cd{};
+                    const bool tr = op->kind == OpKind::kConv3DTranspose;
+                    const Dims& k = op->kernel_dims;
+                    cd.transposed = tr;
+                    cd.k = k.d[0]; cd.v = k.d[1]; cd.c = k.d[2]; cd.r = k.d[3]; cd.s = k.d[4];
+                    for (int i = 0; i < 3; ++i) { cd.stride[i] = op->stride.d[i]; cd.pad[i] = op->pad_start.d[i]; }
+                    for (int i = 0; i < 4; ++i) { cd.in_dims[i] = d.in[0]->dims.d[i]; cd.out_dims[i] = d.out[0]->dims.d[i]; }
+                    cd.weights_dtype = rtType(op->kernel.type); cd.weights = op->kernel.values;
+                    cd.bias = op->bias.count > 0 ? op->bias.values : nullptr;
+                    const char* pe = getenv("REDTAIL_CONV3D_PRECISION");
+                    cd.precision = pe && !strcmp(pe, "fp16") ? RT_PREC_FP16 : pe && !strcmp(pe, "simt") ? RT_PREC_SIMT : RT_PREC_FP32;
+                    TensorImpl* out = d.out[0];
+                    int skip_id = -1;
+                    int nxt = soleConsumer(out);
+                    const OpInfo* no = nxt >= 0 ? opOf(nxt) : nullptr;
+                    if (!tr) {
+                        if (no && no->kind == OpKind::kTransform) {
+                            cd.out_transposed = 1;
+                            done[nxt] = true; out = net.layers_[nxt]->d.out[0]; st.name += " + " + net.layers_[nxt]->d.name;
+                            nxt = soleConsumer(out);
+                        }
+                    } else {
+                        if (no && no->kind == OpKind::kSlice && no->slice_start == 0) {
+                            cd.slice_d = cd.out_dims[0] - no->slice_end;
+                            done[nxt] = true; out = net.layers_[nxt]->d.out[0]; st.name += " + " + net.layers_[nxt]->d.name;
+                            nxt = soleConsumer(out);
+                        }
+                        if (nxt >= 0 && net.layers_[nxt]->d.kind == LKind::kEltwise) {
+                            LayerData& e = net.layers_[nxt]->d;
+                            TensorImpl* other = e.in[0] == out ? e.in[1] : e.in[0];
+                            // the skip tensor must already be produced (it is: layers are in topological order)
+                            if (other != out) {
+                                skip_id = other->id;
+                                done[nxt] = true; out = e.out[0]; st.name += " + " + e.name;
+                                nxt = soleConsumer(out);
+                            }
+                        }
+                    }
+                    if (isFp32Elu(nxt)) {
+                        cd.fuse_elu = 1;
+                        done[nxt] = true; out = net.layers_[nxt]->d.out[0]; st.name += " + " + net.layers_[nxt]->d.name;
+                    }
+                    rt_conv3d_plan* plan = nullptr;
+                    int rc = rt_conv3d_create(&cd, &plan);
+                    if (rc == RT_ERR_UNSUPPORTED && cd.precision != RT_PREC_SIMT) {
+                        logMsg(log_, ILogger::Severity::kWARNING, d.name + ": shape not covered by the tcgen05 kernels, using the fp32 SIMT kernels.");
+                        cd.precision = RT_PREC_SIMT;
+                        rc = rt_conv3d_create(&cd, &plan);
+                    }
+                    if (rc != RT_OK) return fail(d.name + ": rt_conv3d_create failed (" + std::to_string(rc) + ")");
+                    conv3d_plans_.push_back(plan);
+                    st.workspace = rt_conv3d_workspace_size(plan, max_batch_);
+                    const int in_id = d.in[0]->id, out_id = out->id;
+                    if (skip_id >= 0) st.in.push_back(skip_id);
+                    st.out.push_back(out_id);
+                    st.run = [plan, in_id, out_id, skip_id](int batch, const std::function<void*(int)>& ptr, void* ws, cudaStream_t s) {
+                        return rt_conv3d_enqueue(plan, batch, ptr(in_id), skip_id >= 0 ? ptr(skip_id) : nullptr, ptr(out_id), ws, s);
+                    };
+                    break;
+                }
+                // ---- generic plugin protocol ---------------------------------------------------------------------
+                std::vector<Dims> ind, outd;
+                for (auto* t : d.in) ind.push_back(t->dims);
+                for (auto* t : d.out) outd.push_back(t->dims);
+                bool half_io = false;
+                if (d.plugin_ext) {
+                    DataType dt;
+                    if (half2 && d.plugin_ext->supportsFormat(DataType::kHALF, PluginFormat::kNCHW)) dt = DataType::kHALF;
+                    else if (d.plugin_ext->supportsFormat(DataType::kFLOAT, PluginFormat::kNCHW)) dt = DataType::kFLOAT;
+                    else if (d.plugin_ext->supportsFormat(DataType::kHALF, PluginFormat::kNCHW)) dt = DataType::kHALF;
+                    else return fail(d.name + ": plugin supports neither fp32 nor fp16 linear NCHW");
+                    half_io = dt == DataType::kHALF;
+                    d.plugin_ext->configureWithFormat(ind.data(), static_cast<int>(ind.size()), outd.data(),
+                                                      static_cast<int>(outd.size()), dt, PluginFormat::kNCHW, max_batch_);
+                } else {
+                    d.plugin->configure(ind.data(), static_cast<int>(ind.size()), outd.data(), static_cast<int>(outd.size()), max_batch_);
+                }
+                if (d.plugin->initialize() != 0) return fail(d.name + ": plugin initialize() failed");
+                configured_plugins_.push_back(d.plugin);
+                IPlugin* plugin = d.plugin;
+                std::vector<int> in_ids, out_ids;
+                std::vector<size_t> in_elems, out_elems;
+                for (auto* t : d.in) { in_ids.push_back(t->id); in_elems.push_back(slots_[t->id].elems); }
+                for (auto* t : d.out) { out_ids.push_back(t->id); out_elems.push_back(slots_[t->id].elems); st.out.push_back(t->id); }
+                const size_t plug_ws = plugin->getWorkspaceSize(max_batch_);
+                auto align = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
+                size_t conv_bytes = 0;
+                if (half_io) {
+                    for (size_t e : in_elems) conv_bytes += align(e * max_batch_ * 2);
+                    for (size_t e : out_elems) conv_bytes += align(e * max_batch_ * 2);
+                }
+                st.workspace = conv_bytes + plug_ws;
+                const int mb = max_batch_;
+                st.run = [=](int batch, const std::function<void*(int)>& ptr, void* ws, cudaStream_t s) -> int {
+                    std::vector<const void*> in(in_ids.size());
+                    std::vector<void*> out(out_ids.size());
+                    char* w = static_cast<char*>(ws);
+                    if (!half_io) {
+                        for (size_t i = 0; i < in_ids.size(); ++i) in[i] = ptr(in_ids[i]);
+                        for (size_t i = 0; i < out_ids.size(); ++i) out[i] = ptr(out_ids[i]);
+                        return plugin->enqueue(batch, in.data(), out.data(), w, s);
+                    }
+                    // fp16 plugin inside an fp32 graph: reformat in, run, reformat out (what TensorRT's reformat layers do).
+                    for (size_t i = 0; i < in_ids.size(); ++i) {
+                        int rc = rt_convert(RT_F32, ptr(in_ids[i]), RT_F16, w, static_cast<int64_t>(in_elems[i]) * batch, s);
+                        if (rc) return rc;
+                        in[i] = w;
+                        w += (in_elems[i] * mb * 2 + 255) & ~static_cast<size_t>(255);
+                    }
+                    for (size_t i = 0; i < out_ids.size(); ++i) {
+                        out[i] = w;
+                        w += (out_elems[i] * mb * 2 + 255) & ~static_cast<size_t>(255);
+                    }
+                    int rc = plugin->enqueue(batch, in.data(), out.data(), w, s);
+                    if (rc) return rc;
+                    for (size_t i = 0; i < out_ids.size(); ++i) {
+                        rc = rt_convert(RT_F16, out[i], RT_F32, ptr(out_ids[i]), static_cast<int64_t>(out_elems[i]) * batch, s);
+                        if (rc) return rc;
+                    }
+                    return 0;
+                };
+                break;
+            }
+        }
+        steps_.push_back(std::move(st));
+    }
+    return planMemory();
+}
+
+bool EngineImpl::planMemory()
+{
+    auto root = [&](int id) {
+        while (slots_[id].alias_of >= 0) id = slots_[id].alias_of;
+        return id;
+    };
+    // Liveness over steps, on alias roots.
+    for (size_t si = 0; si < steps_.size(); ++si) {
+        for (int id : steps_[si].in) {
+            TensorSlot& s = slots_[root(id)];
+            if (s.first < 0) s.first = static_cast<int>(si);
+            s.last = static_cast<int>(si); s.used = true;
+        }
+        for (int id : steps_[si].out) {
+            TensorSlot& s = slots_[root(id)];
+            if (s.first < 0) s.first = static_cast<int>(si);
+            s.last = std::max(s.last, static_cast<int>(si)); s.used = true;
+        }
+    }
+    // A binding that aliases (through a reshape) to an arena tensor would need a copy; reject the exotic case.
+    for (size_t i = 0; i < slots_.size(); ++i)
+        if (slots_[i].alias_of >= 0 && slots_[i].binding >= 0) return fail("reshape output bound as network output");
+    // First-fit over tensors sorted by size (descending); two tensors may overlap in memory iff their live ranges do not.
+    std::vector<int> order;
+    for (size_t i = 0; i < slots_.size(); ++i)
+        if (slots_[i].used && slots_[i].binding < 0 && slots_[i].alias_of < 0) order.push_back(static_cast<int>(i));
+    auto bytesOf = [&](int id) { return (slots_[id].elems * max_batch_ * sizeof(float) + 255) & ~static_cast<size_t>(255); };
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return bytesOf(a) > bytesOf(b); });
+    std::vector<int> placed;
+    arena_bytes_ = 0;
+    for (int id : order) {
+        const size_t sz = bytesOf(id);
+        std::vector<std::pair<size_t, size_t>> busy;   // [begin, end) of time-overlapping placed tensors
+        for (int p : placed)
+            if (!(slots_[p].last < slots_[id].first || slots_[id].last < slots_[p].first))
+                busy.emplace_back(slots_[p].offset, slots_[p].offset + bytesOf(p));
+        std::sort(busy.begin(), busy.end());
+        size_t off = 0;
+        for (auto& b : busy) {
+            if (off + sz <= b.first) break;
+            off = std::max(off, b.second);
+        }
+        slots_[id].offset = off;
+        arena_bytes_ = std::max(arena_bytes_, off + sz);
+        placed.push_back(id);
+    }
+    workspace_bytes_ = 0;
+    for (auto& s : steps_) workspace_bytes_ = std::max(workspace_bytes_, s.workspace);
+    if (arena_bytes_ > 0 && cudaMalloc(&arena_, arena_bytes_) != cudaSuccess) return fail("cudaMalloc of the activation arena failed");
+    if (workspace_bytes_ > 0 && cudaMalloc(&workspace_, workspace_bytes_) != cudaSuccess) return fail("cudaMalloc of the workspace failed");
+    logMsg(log_, ILogger::Severity::kINFO, "engine: " + std::to_string(steps_.size()) + " steps, activation arena " +
+                                               std::to_string(arena_bytes_ >> 20) + " MiB, workspace " + std::to_string(workspace_bytes_ >> 20) + " MiB");
+    return true;
+}
+
+bool ContextImpl::run(int batchSize, void** bindings, cudaStream_t stream, bool profile)
+{
+    EngineImpl& e = *engine_;
+    if (batchSize < 1 || batchSize > e.max_batch_ || bindings == nullptr) {
+        logMsg(e.log_, ILogger::Severity::kERROR, "execute: invalid batch size or bindings");
+        return false;
+    }
+    std::function<void*(int)> ptr = [&](int id) -> void* {
+        while (e.slots_[id].alias_of >= 0) id = e.slots_[id].alias_of;
+        const TensorSlot& s = e.slots_[id];
+        if (s.binding >= 0) return bindings[s.binding];
+        return static_cast<char*>(e.arena_) + s.offset;
+    };
+    std::vector<cudaEvent_t> ev;
+    if (profile) {
+        ev.resize(e.steps_.size() + 1);
+        for (auto& x : ev) cudaEventCreate(&x);
+        cudaEventRecord(ev[0], stream);
+    }
+    bool ok = true;
+    for (size_t i = 0; i < e.steps_.size(); ++i) {
+        const int rc = e.steps_[i].run(batchSize, ptr, e.workspace_, stream);
+        if (rc != 0) {
+            logMsg(e.log_, ILogger::Severity::kERROR, e.steps_[i].name + ": enqueue failed with status " + std::to_string(rc));
+            ok = false;
+            break;
+        }
+        if (debug_sync_ && cudaStreamSynchronize(stream) != cudaSuccess) { ok = false; break; }
+        if (profile) cudaEventRecord(ev[i + 1], stream);
+    }
+    if (profile) {
+        cudaStreamSynchronize(stream);
+        for (size_t i = 0; ok && i < e.steps_.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            profiler_->reportLayerTime(e.steps_[i].name.c_str(), ms);
+        }
+        for (auto& x : ev) cudaEventDestroy(x);
+    }
+    return ok;
+}
+
+bool ContextImpl::execute(int batchSize, void** bindings)
+{
+    // The caller's copies ran on the legacy default stream (cudaMemcpy): they are complete by the time we are called.
+    const bool ok = run(batchSize, bindings, stream_, profiler_ != nullptr);
+    const cudaError_t err = cudaStreamSynchronize(stream_);
+    if (err != cudaSuccess) {
+        logMsg(engine_->log_, ILogger::Severity::kERROR, std::string("execute: ") + cudaGetErrorString(err));
+        return false;
+    }
+    return ok;
+}
+
+bool ContextImpl::enqueue(int batchSize, void** bindings, cudaStream_t stream, cudaEvent_t* inputConsumed)
+{
+    const bool ok = run(batchSize, bindings, stream, false);
+    if (inputConsumed) cudaEventRecord(*inputConsumed, stream);
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Builder / runtime
+// ------------------------------------------------------------------------------------------------------------------
+class BuilderImpl : public IBuilder {
+public:
+    explicit BuilderImpl(ILogger& log) : log_(log) {}
+    INetworkDefinition* createNetwork() override { return new NetworkImpl(log_); }
+    void setMaxBatchSize(int b) override { max_batch_ = b; }
+    int getMaxBatchSize() const override { return max_batch_; }
+    void setMaxWorkspaceSize(size_t w) override { max_ws_ = w; }
+    size_t getMaxWorkspaceSize() const override { return max_ws_; }
+    void setHalf2Mode(bool m) override { half2_ = m; }
+    bool getHalf2Mode() const override { return half2_; }
+    void setDebugSync(bool s) override { debug_sync_ = s; }
+    bool getDebugSync() const override { return debug_sync_; }
+    void setMinFindIterations(int n) override { min_find_ = n; }
+    int getMinFindIterations() const override { return min_find_; }
+    void setAverageFindIterations(int n) override { avg_find_ = n; }
+    int getAverageFindIterations() const override { return avg_find_; }
+    ICudaEngine* buildCudaEngine(INetworkDefinition& network) override
+    {
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+            logMsg(log_, ILogger::Severity::kERROR, "buildCudaEngine: no CUDA device (this engine has no CPU path).");
+            return nullptr;
+        }
+        auto* e = new EngineImpl(log_);
+        if (!e->build(static_cast<NetworkImpl&>(network), max_batch_, half2_)) {
+            delete e;
+            return nullptr;
+        }
+        return e;
+    }
+    bool platformHasFastFp16() const override { return true; }
+    bool platformHasFastInt8() const override { return false; }
+    void destroy() override { delete this; }
+
+private:
+    ILogger& log_;
+    int max_batch_ = 1, min_find_ = 1, avg_find_ = 1;
+    size_t max_ws_ = 0;
+    bool half2_ = false, debug_sync_ = false;
+};
+
+class RuntimeImpl : public IRuntime {
+public:
+    explicit RuntimeImpl(ILogger& log) : log_(log) {}
+    ICudaEngine* deserializeCudaEngine(const void*, size_t, IPluginFactory*) override
+    {
+        logMsg(log_, ILogger::Severity::kERROR, "deserializeCudaEngine: engine plans are not serialisable in this build.");
+        return nullptr;
+    }
+    void destroy() override { delete this; }
+
+private:
+    ILogger& log_;
+};
+
+}  // namespace
+
+extern "C" void* createInferBuilder_INTERNAL(void* logger, int)
+{
+    return static_cast<IBuilder*>(new BuilderImpl(*static_cast<ILogger*>(logger)));
+}
+
+extern "C" void* createInferRuntime_INTERNAL(void* logger, int)
+{
+    return static_cast<IRuntime*>(new RuntimeImpl(*static_cast<ILogger*>(logger)));
+}

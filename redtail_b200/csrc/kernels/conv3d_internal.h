@@ -1,0 +1,31 @@
+// Internal plan object shared by the SIMT validation path (conv3d_simt.cu) and the tcgen05 path (conv3d_tc.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "redtail_b200.h"
+
+struct rt_conv3d_plan {
+    rt_conv3d_desc desc;
+    // Output geometry actually written (transposed conv: out_dims[0] - slice_d planes).
+    int out_planes;
+    // ---- SIMT path: weights repacked to [ceil(Cout/16)][V][Cin][R][S][16] fp32, bias fp32 [Cout] (zeros if absent).
+    float* w_simt = nullptr;
+    float* bias = nullptr;
+    int cout = 0, cin = 0;
+    // ---- tcgen05 path (filled by rt::tc_plan_init when precision != RT_PREC_SIMT and the shape is supported).
+    void* tc = nullptr;
+};
+
+namespace rt {
+int simt_conv3d_enqueue(const rt_conv3d_plan* p, int n, const float* x, const float* skip, float* y, cudaStream_t s);
+// Returns RT_OK and sets p->tc, or RT_ERR_UNSUPPORTED when the shape is outside what the tensor-core kernels cover
+// (the caller then fails loudly -- there is no silent fallback from a requested tensor-core precision).
+int tc_plan_init(rt_conv3d_plan* p, const std::vector<float>& w_kvcrs, const std::vector<float>& bias);
+void tc_plan_destroy(rt_conv3d_plan* p);
+size_t tc_workspace_size(const rt_conv3d_plan* p, int max_batch);
+int tc_conv3d_enqueue(const rt_conv3d_plan* p, int n, const float* x, const float* skip, float* y, void* workspace,
+                      cudaStream_t s);
+}  // namespace rt

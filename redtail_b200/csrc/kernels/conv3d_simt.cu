@@ -1,0 +1,329 @@
+// 3-D convolution / transposed convolution plans (Conv3DPlugin, Conv3DTransposePlugin) -- plan management and the
+// fp32 CUDA-core kernels (RT_PREC_SIMT).  The tensor-core kernels live in conv3d_tc.cu; this file is the exact-fp32
+// validation path they are checked against on the device, and the path for shapes the tcgen05 tiles do not cover
+// (channel counts that are not multiples of 16, e.g. the reference's tiny unit-test tensors).
+//
+// Semantics (reference): lib/conv3d_plugin.cpp:74-100,187-216 + lib/conv_utils.cpp:14-81 (cuDNN cross-correlation,
+// symmetric pad = pad_start, input [D,C,H,W], output [K,Do,Ho,Wo], bias over K);
+// lib/conv3d_transpose_plugin.cpp:86-114,205-243 (cudnnConvolutionBackwardData: input [K,Dy,Hy,Wy], output
+// [Dx,C,Hx,Wx] of caller-supplied out_dims, bias over C -- lib/kernels.cu:292-308).
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "conv3d_internal.h"
+
+namespace rt {
+namespace {
+
+constexpr int KT = 16;          // output channels per thread
+constexpr int kThreads = 128;   // output x positions per CTA
+
+struct ConvGeom {
+    int cin, cout;              // conv: C -> K ; transposed: K -> C
+    int v, r, s;
+    int sd, sh, sw, pd, ph, pw;
+    int di, hi, wi;             // input spatial extent
+    int dout, ho, wo;           // output spatial extent actually written
+    int fuse_elu, out_transposed;
+};
+
+__device__ __forceinline__ float4 ldw(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// Forward conv.  x [Di, Cin, Hi, Wi];  w packed [Cout/16][V][Cin][R][S][16];  y [Cout, Do, Ho, Wo] (or [Do, Cout, Ho, Wo]).
+__global__ void __launch_bounds__(kThreads)
+conv3d_fwd_simt_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                       const float* __restrict__ skip, float* __restrict__ y, ConvGeom g, int ktiles) {
+    const int wo = blockIdx.x * kThreads + threadIdx.x;
+    const int ho = blockIdx.y;
+    int z = blockIdx.z;
+    const int kt = z % ktiles; z /= ktiles;
+    const int dd = z % g.dout;
+    const int n = z / g.dout;
+    const int64_t in_plane = static_cast<int64_t>(g.hi) * g.wi;
+    const float* xn = x + static_cast<int64_t>(n) * g.di * g.cin * in_plane;
+    const float* wk = w + static_cast<int64_t>(kt) * g.v * g.cin * g.r * g.s * KT;
+    float acc[KT];
+#pragma unroll
+    for (int i = 0; i < KT; ++i) acc[i] = 0.f;
+    const bool active = wo < g.wo;
+    for (int v = 0; v < g.v; ++v) {
+        const int d_in = dd * g.sd + v - g.pd;
+        if (d_in < 0 || d_in >= g.di) continue;
+        for (int c = 0; c < g.cin; ++c) {
+            const float* xp = xn + (static_cast<int64_t>(d_in) * g.cin + c) * in_plane;
+            const float* wp = wk + (static_cast<int64_t>(v) * g.cin + c) * g.r * g.s * KT;
+            for (int r = 0; r < g.r; ++r) {
+                const int h_in = ho * g.sh + r - g.ph;
+                if (h_in < 0 || h_in >= g.hi) continue;
+                for (int s = 0; s < g.s; ++s) {
+                    const int w_in = wo * g.sw + s - g.pw;
+                    const float xv = (active && w_in >= 0 && w_in < g.wi) ? __ldg(xp + static_cast<int64_t>(h_in) * g.wi + w_in) : 0.f;
+                    const float* wq = wp + (r * g.s + s) * KT;
+#pragma unroll
+                    for (int q = 0; q < KT / 4; ++q) {
+                        const float4 wv = ldw(wq + 4 * q);
+                        acc[4 * q + 0] = fmaf(wv.x, xv, acc[4 * q + 0]);
+                        acc[4 * q + 1] = fmaf(wv.y, xv, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(wv.z, xv, acc[4 * q + 2]);
+                        acc[4 * q + 3] = fmaf(wv.w, xv, acc[4 * q + 3]);
+                    }
+                }
+            }
+        }
+    }
+    if (!active) return;
+    const int64_t out_plane = static_cast<int64_t>(g.ho) * g.wo;
+    const int64_t nout = static_cast<int64_t>(n) * g.cout * g.dout * out_plane;
+#pragma unroll
+    for (int i = 0; i < KT; ++i) {
+        const int k = kt * KT + i;
+        if (k >= g.cout) break;
+        const int64_t idx = nout + (g.out_transposed ? (static_cast<int64_t>(dd) * g.cout + k) : (static_cast<int64_t>(k) * g.dout + dd)) * out_plane +
+                            static_cast<int64_t>(ho) * g.wo + wo;
+        float vv = acc[i] + bias[k];
+        if (skip) vv += skip[idx];
+        if (g.fuse_elu) vv = elu1(vv);
+        y[idx] = vv;
+    }
+}
+
+// Transposed conv (gather form of the data gradient).  yin [K, Dy, Hy, Wy];  w packed [C/16][V][K][R][S][16];
+// x out [Dx, C, Hx, Wx]:  x[dx,c,hx,wx] = b[c] + sum_{k,v,r,s} w[k,v,c,r,s] * yin[k,(dx+pd-v)/sd,(hx+ph-r)/sh,(wx+pw-s)/sw]
+// over the taps where the divisions are exact and in range.
+__global__ void __launch_bounds__(kThreads)
+conv3d_bwd_simt_kernel(const float* __restrict__ yin, const float* __restrict__ w, const float* __restrict__ bias,
+                       const float* __restrict__ skip, float* __restrict__ x, ConvGeom g, int ctiles) {
+    const int wx = blockIdx.x * kThreads + threadIdx.x;
+    const int hx = blockIdx.y;
+    int z = blockIdx.z;
+    const int ct = z % ctiles; z /= ctiles;
+    const int dx = z % g.dout;
+    const int n = z / g.dout;
+    const int64_t in_plane = static_cast<int64_t>(g.hi) * g.wi;
+    const float* yn = yin + static_cast<int64_t>(n) * g.cin * g.di * in_plane;
+    const float* wc = w + static_cast<int64_t>(ct) * g.v * g.cin * g.r * g.s * KT;
+    float acc[KT];
+#pragma unroll
+    for (int i = 0; i < KT; ++i) acc[i] = 0.f;
+    const bool active = wx < g.wo;
+    for (int v = 0; v < g.v; ++v) {
+        const int td = dx + g.pd - v;
+        if (td < 0 || td % g.sd) continue;
+        const int dy = td / g.sd;
+        if (dy >= g.di) continue;
+        for (int r = 0; r < g.r; ++r) {
+            const int th = hx + g.ph - r;
+            if (th < 0 || th % g.sh) continue;
+            const int hy = th / g.sh;
+            if (hy >= g.hi) continue;
+            for (int s = 0; s < g.s; ++s) {
+                const int tw = wx + g.pw - s;
+                const bool ok = active && tw >= 0 && (tw % g.sw) == 0 && (tw / g.sw) < g.wi;
+                const int wy = ok ? tw / g.sw : 0;
+                for (int k = 0; k < g.cin; ++k) {
+                    const float yv = ok ? __ldg(yn + (static_cast<int64_t>(k) * g.di + dy) * in_plane + static_cast<int64_t>(hy) * g.wi + wy) : 0.f;
+                    const float* wq = wc + ((static_cast<int64_t>(v) * g.cin + k) * g.r * g.s + r * g.s + s) * KT;
+#pragma unroll
+                    for (int q = 0; q < KT / 4; ++q) {
+                        const float4 wv = ldw(wq + 4 * q);
+                        acc[4 * q + 0] = fmaf(wv.x, yv, acc[4 * q + 0]);
+                        acc[4 * q + 1] = fmaf(wv.y, yv, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(wv.z, yv, acc[4 * q + 2]);
+                        acc[4 * q + 3] = fmaf(wv.w, yv, acc[4 * q + 3]);
+                    }
+                }
+            }
+        }
+    }
+    if (!active) return;
+    const int64_t out_plane = static_cast<int64_t>(g.ho) * g.wo;
+    const int64_t nout = static_cast<int64_t>(n) * g.dout * g.cout * out_plane;
+#pragma unroll
+    for (int i = 0; i < KT; ++i) {
+        const int c = ct * KT + i;
+        if (c >= g.cout) break;
+        const int64_t idx = nout + (static_cast<int64_t>(dx) * g.cout + c) * out_plane + static_cast<int64_t>(hx) * g.wo + wx;
+        float vv = acc[i] + bias[c];
+        if (skip) vv += skip[idx];
+        if (g.fuse_elu) vv = elu1(vv);
+        x[idx] = vv;
+    }
+}
+
+ConvGeom make_geom(const rt_conv3d_plan* p) {
+    const rt_conv3d_desc& d = p->desc;
+    ConvGeom g{};
+    g.v = d.v; g.r = d.r; g.s = d.s;
+    g.sd = d.stride[0]; g.sh = d.stride[1]; g.sw = d.stride[2];
+    g.pd = d.pad[0]; g.ph = d.pad[1]; g.pw = d.pad[2];
+    g.fuse_elu = d.fuse_elu;
+    g.out_transposed = d.out_transposed;
+    if (!d.transposed) {
+        g.cin = d.c; g.cout = d.k;
+        g.di = d.in_dims[0]; g.hi = d.in_dims[2]; g.wi = d.in_dims[3];
+        g.dout = d.out_dims[1]; g.ho = d.out_dims[2]; g.wo = d.out_dims[3];
+    } else {
+        g.cin = d.k; g.cout = d.c;
+        g.di = d.in_dims[1]; g.hi = d.in_dims[2]; g.wi = d.in_dims[3];
+        g.dout = p->out_planes; g.ho = d.out_dims[2]; g.wo = d.out_dims[3];
+    }
+    return g;
+}
+
+}  // namespace
+
+int simt_conv3d_enqueue(const rt_conv3d_plan* p, int n, const float* x, const float* skip, float* y, cudaStream_t s) {
+    const ConvGeom g = make_geom(p);
+    const int tiles = (g.cout + KT - 1) / KT;
+    const int64_t gz = static_cast<int64_t>(n) * g.dout * tiles;
+    if (gz > 65535 * 32 || g.ho > 65535) return RT_ERR_UNSUPPORTED;
+    // gridDim.z is limited to 65535: fold the overflow into several launches over n.
+    const int per_launch_n = gz <= 65535 ? n : static_cast<int>(65535 / (static_cast<int64_t>(g.dout) * tiles));
+    if (per_launch_n < 1) return RT_ERR_UNSUPPORTED;
+    const int64_t in_elems = static_cast<int64_t>(p->desc.in_dims[0]) * p->desc.in_dims[1] * p->desc.in_dims[2] * p->desc.in_dims[3];
+    const int64_t out_elems = static_cast<int64_t>(g.cout) * g.dout * g.ho * g.wo;
+    for (int n0 = 0; n0 < n; n0 += per_launch_n) {
+        const int nn = (n - n0) < per_launch_n ? (n - n0) : per_launch_n;
+        dim3 grid((g.wo + kThreads - 1) / kThreads, g.ho, nn * g.dout * tiles);
+        const float* xs = x + n0 * in_elems;
+        const float* ss = skip ? skip + n0 * out_elems : nullptr;
+        float* ys = y + n0 * out_elems;
+        if (!p->desc.transposed)
+            conv3d_fwd_simt_kernel<<<grid, kThreads, 0, s>>>(xs, p->w_simt, p->bias, ss, ys, g, tiles);
+        else
+            conv3d_bwd_simt_kernel<<<grid, kThreads, 0, s>>>(xs, p->w_simt, p->bias, ss, ys, g, tiles);
+        note_launch(p->desc.transposed ? "conv3d_transpose_simt" : "conv3d_simt");
+        RT_CHECK_LAUNCH();
+    }
+    return RT_OK;
+}
+
+}  // namespace rt
+
+using namespace rt;
+
+namespace {
+
+float half_bits_to_float(uint16_t h) {
+    const uint32_t sign = (h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1F, man = h & 0x3FF, bits;
+    if (exp == 0) {
+        if (man == 0) bits = sign;
+        else {
+            int e = -1;
+            do { man <<= 1; ++e; } while (!(man & 0x400));
+            bits = sign | ((127 - 15 - e) << 23) | ((man & 0x3FF) << 13);
+        }
+    } else if (exp == 31) bits = sign | 0x7F800000u | (man << 13);
+    else bits = sign | ((exp + 112) << 23) | (man << 13);
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+
+void host_to_f32(int dtype, const void* src, int64_t count, std::vector<float>& dst) {
+    dst.resize(count);
+    if (dtype == RT_F32) memcpy(dst.data(), src, count * 4);
+    else {
+        const uint16_t* h = static_cast<const uint16_t*>(src);
+        for (int64_t i = 0; i < count; ++i) dst[i] = half_bits_to_float(h[i]);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_conv3d_create(const rt_conv3d_desc* d, rt_conv3d_plan** out) {
+    if (!d || !out || !d->weights) return RT_ERR_ARG;
+    if (d->k <= 0 || d->v <= 0 || d->c <= 0 || d->r <= 0 || d->s <= 0) return RT_ERR_ARG;
+    for (int i = 0; i < 3; ++i)
+        if (d->stride[i] <= 0 || d->pad[i] < 0) return RT_ERR_ARG;
+    if (d->weights_dtype != RT_F32 && d->weights_dtype != RT_F16) return RT_ERR_UNSUPPORTED;
+    // Shape consistency, as the plugins assert it (conv3d_plugin.cpp:82-100, conv3d_transpose_plugin.cpp:104-108).
+    const int* conv_in = d->transposed ? d->out_dims : d->in_dims;     // [D, C, H, W] of the forward conv
+    const int* conv_out = d->transposed ? d->in_dims : d->out_dims;    // [K, Do, Ho, Wo]
+    if (conv_in[1] != d->c || conv_out[0] != d->k) return RT_ERR_ARG;
+    const int kk[3] = {d->v, d->r, d->s};
+    const int sp_in[3] = {conv_in[0], conv_in[2], conv_in[3]};
+    for (int i = 0; i < 3; ++i) {
+        const int span = sp_in[i] + 2 * d->pad[i] - kk[i];
+        if (span < 0 || span / d->stride[i] + 1 != conv_out[1 + i]) return RT_ERR_ARG;
+    }
+    if (d->transposed && (d->slice_d < 0 || d->slice_d >= d->out_dims[0])) return RT_ERR_ARG;
+    if (!d->transposed && d->slice_d != 0) return RT_ERR_ARG;
+    if (d->transposed && d->out_transposed) return RT_ERR_ARG;
+
+    rt_conv3d_plan* p = new rt_conv3d_plan();
+    p->desc = *d;
+    p->desc.weights = nullptr;
+    p->desc.bias = nullptr;
+    p->out_planes = d->transposed ? d->out_dims[0] - d->slice_d : d->out_dims[1];
+    p->cout = d->transposed ? d->c : d->k;
+    p->cin = d->transposed ? d->k : d->c;
+
+    const int64_t wcount = static_cast<int64_t>(d->k) * d->v * d->c * d->r * d->s;
+    std::vector<float> w, b;
+    host_to_f32(d->weights_dtype, d->weights, wcount, w);
+    if (d->bias) host_to_f32(d->weights_dtype, d->bias, p->cout, b);
+    else b.assign(p->cout, 0.f);
+
+    // SIMT packing: [ceil(Cout/16)][V][Cin][R][S][16], zero padded.
+    const int tiles = (p->cout + 15) / 16;
+    std::vector<float> pk(static_cast<size_t>(tiles) * d->v * p->cin * d->r * d->s * 16, 0.f);
+    for (int k = 0; k < d->k; ++k)
+        for (int v = 0; v < d->v; ++v)
+            for (int c = 0; c < d->c; ++c)
+                for (int r = 0; r < d->r; ++r)
+                    for (int s = 0; s < d->s; ++s) {
+                        const float val = w[(((static_cast<int64_t>(k) * d->v + v) * d->c + c) * d->r + r) * d->s + s];
+                        const int co = d->transposed ? c : k, ci = d->transposed ? k : c;
+                        const int64_t idx = ((((static_cast<int64_t>(co / 16) * d->v + v) * p->cin + ci) * d->r + r) * d->s + s) * 16 + (co % 16);
+                        pk[idx] = val;
+                    }
+    cudaError_t e = cudaMalloc(&p->w_simt, pk.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(p->w_simt, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&p->bias, b.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(p->bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        rt_conv3d_destroy(p);
+        return static_cast<int>(e);
+    }
+    if (d->precision != RT_PREC_SIMT) {
+        const int rc = tc_plan_init(p, w, b);
+        if (rc != RT_OK) {           // no silent downgrade of a requested tensor-core precision
+            rt_conv3d_destroy(p);
+            return rc;
+        }
+    }
+    *out = p;
+    return RT_OK;
+}
+
+void rt_conv3d_destroy(rt_conv3d_plan* p) {
+    if (!p) return;
+    tc_plan_destroy(p);
+    cudaFree(p->w_simt);
+    cudaFree(p->bias);
+    delete p;
+}
+
+size_t rt_conv3d_workspace_size(const rt_conv3d_plan* p, int max_batch) {
+    if (!p || !p->tc) return 0;
+    return tc_workspace_size(p, max_batch);
+}
+
+int rt_conv3d_enqueue(const rt_conv3d_plan* p, int n, const void* x, const void* skip, void* y, void* workspace,
+                      void* stream) {
+    if (!p || !x || !y || n < 0) return RT_ERR_ARG;
+    if (n == 0) return RT_OK;
+    if (p->tc)
+        return tc_conv3d_enqueue(p, n, static_cast<const float*>(x), static_cast<const float*>(skip),
+                                 static_cast<float*>(y), workspace, as_stream(stream));
+    return simt_conv3d_enqueue(p, n, static_cast<const float*>(x), static_cast<const float*>(skip),
+                               static_cast<float*>(y), as_stream(stream));
+}
+
+}  // extern "C"

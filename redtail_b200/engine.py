@@ -1,0 +1,80 @@
+"""Python handle on the whole-network C-ABI (include/redtail_b200_engine.h)."""
+import ctypes as C
+
+import torch
+
+from ._lib import engine_lib
+from .ops import RedtailError, RT_F32, RT_F16
+
+MODELS = {"nvsmall": 48, "nvtiny": 24}      # half-resolution max disparity of the reference's weight sets
+
+
+class StereoEngine:
+    """The reference's NVSmall-family stereo net on one GPU.
+
+    left/right: [N,3,H,W] fp32 in [0,1]  ->  disparity [N,H,W] fp32 (pixels).
+    """
+
+    def __init__(self, model, height, width, weights_path, max_batch=1, max_disp=None, weights_dtype="fp32"):
+        if not torch.cuda.is_available():
+            raise RedtailError("StereoEngine needs a CUDA device (there is no CPU path)")
+        self.lib = engine_lib()
+        self.h, self.w, self.max_batch = height, width, max_batch
+        self._e = C.c_void_p()
+        md = max_disp if max_disp is not None else MODELS[model]
+        rc = self.lib.rt_stereo_create(model.encode(), height, width, md, str(weights_path).encode(),
+                                       RT_F16 if weights_dtype == "fp16" else RT_F32, max_batch, C.byref(self._e))
+        if rc != 0:
+            raise RedtailError("rt_stereo_create failed (%d): %s" % (rc, self.lib.rt_stereo_last_error().decode()))
+
+    def __call__(self, left, right, out=None):
+        """Device tensors in, device tensor out; asynchronous on the current torch stream."""
+        assert left.is_cuda and right.is_cuda and left.dtype == torch.float32 and left.is_contiguous() and right.is_contiguous()
+        n = left.shape[0]
+        if out is None:
+            out = torch.empty((n, self.h, self.w), dtype=torch.float32, device=left.device)
+        rc = self.lib.rt_stereo_enqueue(self._e, n, C.c_void_p(left.data_ptr()), C.c_void_p(right.data_ptr()),
+                                        C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise RedtailError("rt_stereo_enqueue failed (%d): %s" % (rc, self.lib.rt_stereo_last_error().decode()))
+        return out
+
+    def execute_host(self, left, right, out):
+        """Host (ideally pinned) tensors: H2D + inference + D2H, synchronous -- the end-to-end call of the apps."""
+        n = left.shape[0]
+        rc = self.lib.rt_stereo_execute_host(self._e, n, C.c_void_p(left.data_ptr()), C.c_void_p(right.data_ptr()),
+                                             C.c_void_p(out.data_ptr()))
+        if rc != 0:
+            raise RedtailError("rt_stereo_execute_host failed (%d): %s" % (rc, self.lib.rt_stereo_last_error().decode()))
+        return out
+
+    def profile(self, left, right):
+        """-> list of (layer name, ms), measured with CUDA events around every engine step."""
+        n = left.shape[0]
+        out = torch.empty((n, self.h, self.w), dtype=torch.float32, device=left.device)
+        buf = C.create_string_buffer(1 << 16)
+        torch.cuda.synchronize()
+        rc = self.lib.rt_stereo_profile(self._e, n, C.c_void_p(left.data_ptr()), C.c_void_p(right.data_ptr()),
+                                        C.c_void_p(out.data_ptr()), buf, len(buf))
+        if rc != 0:
+            raise RedtailError("rt_stereo_profile failed (%d)" % rc)
+        rows = []
+        for line in buf.value.decode().splitlines():
+            name, ms = line.rsplit("\t", 1)
+            rows.append((name, float(ms)))
+        return rows
+
+    @property
+    def num_layers(self):
+        return self.lib.rt_stereo_num_layers(self._e)
+
+    def close(self):
+        if getattr(self, "_e", None):
+            self.lib.rt_stereo_destroy(self._e)
+            self._e = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,272 @@
+"""Python mirror of the plugin-level C-ABI (include/redtail_b200.h) on torch CUDA tensors.
+
+Argument meaning follows the reference plugins (stereoDNN/lib/*_plugin.cpp); tensors carry a leading batch dim.
+Every function launches the library's CUDA kernels on the current torch stream; nothing here computes on the host.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import kernels_lib, Conv3dDesc, Conv2dDesc
+
+RT_F32, RT_F16 = 0, 1
+PREC_FP32, PREC_FP16, PREC_SIMT = 0, 1, 2
+
+
+class RedtailError(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RedtailError("%s failed with status %d" % (what, rc))
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return RT_F32
+    if t.dtype == torch.float16:
+        return RT_F16
+    raise TypeError("unsupported dtype %s" % t.dtype)
+
+
+def _dev(*ts):
+    for t in ts:
+        if t is not None and not (t.is_cuda and t.is_contiguous()):
+            raise ValueError("redtail_b200 ops need contiguous CUDA tensors (there is no CPU path)")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def cost_volume(left, right, max_disp):
+    """[N,C,H,W] x2 -> [N,D,2C,H,W]   (CostVolumePlugin kDefault)."""
+    _dev(left, right)
+    n, c, h, w = left.shape
+    out = torch.empty((n, max_disp, 2 * c, h, w), dtype=left.dtype, device=left.device)
+    _check(kernels_lib().rt_cost_volume(_dt(left), _p(left), _p(right), _p(out), n, c, h, w, max_disp, _stream()), "rt_cost_volume")
+    return out
+
+
+def corr_cost_volume(left, right, max_disp):
+    """[N,C,H,W] x2 -> [N,D,H,W]   (CostVolumePlugin kCorrelation)."""
+    _dev(left, right)
+    n, c, h, w = left.shape
+    out = torch.empty((n, max_disp, h, w), dtype=left.dtype, device=left.device)
+    _check(kernels_lib().rt_corr_cost_volume(_dt(left), _p(left), _p(right), _p(out), n, c, h, w, max_disp, _stream()), "rt_corr_cost_volume")
+    return out
+
+
+def elu(x):
+    _dev(x)
+    y = torch.empty_like(x)
+    _check(kernels_lib().rt_elu(_dt(x), _p(x), _p(y), x.numel(), _stream()), "rt_elu")
+    return y
+
+
+def sigmoid(x):
+    _dev(x)
+    y = torch.empty_like(x)
+    _check(kernels_lib().rt_sigmoid(_dt(x), _p(x), _p(y), x.numel(), _stream()), "rt_sigmoid")
+    return y
+
+
+def scale(x, shift, scl, power):
+    _dev(x)
+    y = torch.empty_like(x)
+    _check(kernels_lib().rt_scale(_dt(x), _p(x), _p(y), x.numel(), shift, scl, power, _stream()), "rt_scale")
+    return y
+
+
+def eltwise_sum(a, b):
+    _dev(a, b)
+    y = torch.empty_like(a)
+    _check(kernels_lib().rt_eltwise_sum(_dt(a), _p(a), _p(b), _p(y), a.numel(), _stream()), "rt_eltwise_sum")
+    return y
+
+
+def convert(x, dtype):
+    _dev(x)
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    _check(kernels_lib().rt_convert(_dt(x), _p(x), _dt(y), _p(y), x.numel(), _stream()), "rt_convert")
+    return y
+
+
+def pad_d(x, pad_end):
+    """[N,D,...] -> [N,D+pad_end,...], zero planes appended (PaddingPlugin)."""
+    _dev(x)
+    n, d = x.shape[:2]
+    plane = int(np.prod(x.shape[2:]))
+    y = torch.empty((n, d + pad_end) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
+    _check(kernels_lib().rt_pad_planes(_dt(x), _p(x), _p(y), n, d, plane, pad_end, _stream()), "rt_pad_planes")
+    return y
+
+
+def slice_d(x, start, end):
+    """[N,D,...] -> [N,end-start,...] (SlicePlugin)."""
+    _dev(x)
+    n, d = x.shape[:2]
+    plane = int(np.prod(x.shape[2:]))
+    y = torch.empty((n, end - start) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
+    _check(kernels_lib().rt_slice_planes(_dt(x), _p(x), _p(y), n, d, plane, start, end, _stream()), "rt_slice_planes")
+    return y
+
+
+def transform(x):
+    """[N,A,B,H,W] -> [N,B,A,H,W] (TransformPlugin {1,0,2,3})."""
+    _dev(x)
+    n, a, b = x.shape[:3]
+    inner = int(np.prod(x.shape[3:]))
+    y = torch.empty((n, b, a) + tuple(x.shape[3:]), dtype=x.dtype, device=x.device)
+    _check(kernels_lib().rt_transpose01(_dt(x), _p(x), _p(y), n, a, b, inner, _stream()), "rt_transpose01")
+    return y
+
+
+def concat_channels(a, b):
+    _dev(a, b)
+    n, ca = a.shape[:2]
+    cb = b.shape[1]
+    inner = int(np.prod(a.shape[2:]))
+    y = torch.empty((n, ca + cb) + tuple(a.shape[2:]), dtype=a.dtype, device=a.device)
+    _check(kernels_lib().rt_concat_channels(_dt(a), _p(a), ca, _p(b), cb, _p(y), n, inner, _stream()), "rt_concat_channels")
+    return y
+
+
+def softargmax(x, is_min):
+    """[N,D,1,H,W] or [N,D,H,W] -> [N,1,H,W] (SoftargmaxPlugin)."""
+    _dev(x)
+    if x.dim() == 5:
+        assert x.shape[2] == 1
+        x = x[:, :, 0]
+    n, d, h, w = x.shape
+    y = torch.empty((n, 1, h, w), dtype=x.dtype, device=x.device)
+    _check(kernels_lib().rt_softargmax(_dt(x), int(bool(is_min)), _p(x), _p(y), n, d, h * w, _stream()), "rt_softargmax")
+    return y
+
+
+class Conv3d:
+    """Conv3DPlugin / Conv3DTransposePlugin plan (weights are repacked and uploaded once, like the plugin's configure()).
+
+    conv      : x [N,D,C,H,W]  -> y [N,K,Do,Ho,Wo]   (or [N,Do,K,Ho,Wo] with out_transposed)
+    transposed: y [N,K,Dy,Hy,Wy] -> x [N,Dx-slice_d,C,Hx,Wx]   with out_dims = (Dx,C,Hx,Wx)
+    """
+
+    def __init__(self, weights, bias, stride, pad_start, in_dims, out_dims=None, transposed=False,
+                 precision=PREC_FP32, fuse_elu=False, out_transposed=False, slice_d=0):
+        w = np.ascontiguousarray(weights)
+        assert w.ndim == 5 and w.dtype in (np.float32, np.float16)
+        b = None if bias is None else np.ascontiguousarray(bias).astype(w.dtype)
+        k, v, c, r, s = w.shape
+        d = Conv3dDesc()
+        d.transposed = int(transposed)
+        d.k, d.v, d.c, d.r, d.s = k, v, c, r, s
+        d.stride[:] = list(stride)
+        d.pad[:] = list(pad_start)
+        d.in_dims[:] = list(in_dims)
+        if not transposed:
+            sp = (in_dims[0], in_dims[2], in_dims[3])
+            kk = (v, r, s)
+            o = [(sp[i] + 2 * pad_start[i] - kk[i]) // stride[i] + 1 for i in range(3)]
+            out_dims = (k, o[0], o[1], o[2])
+        d.out_dims[:] = list(out_dims)
+        d.weights_dtype = RT_F32 if w.dtype == np.float32 else RT_F16
+        d.weights = w.ctypes.data
+        d.bias = b.ctypes.data if b is not None else None
+        d.precision = precision
+        d.fuse_elu = int(fuse_elu)
+        d.out_transposed = int(out_transposed)
+        d.slice_d = int(slice_d)
+        self.desc = d
+        self.transposed = transposed
+        self.out_dims = tuple(out_dims)
+        self._plan = C.c_void_p()
+        rc = kernels_lib().rt_conv3d_create(C.byref(d), C.byref(self._plan))
+        if rc != 0:
+            raise RedtailError("rt_conv3d_create failed with status %d" % rc)
+        self._ws = None
+
+    def __call__(self, x, skip=None):
+        _dev(x, skip)
+        assert x.dtype == torch.float32
+        n = x.shape[0]
+        assert tuple(x.shape[1:]) == tuple(self.desc.in_dims), (x.shape, tuple(self.desc.in_dims))
+        od = self.out_dims
+        if self.transposed:
+            shape = (n, od[0] - self.desc.slice_d, od[1], od[2], od[3])
+        elif self.desc.out_transposed:
+            shape = (n, od[1], od[0], od[2], od[3])
+        else:
+            shape = (n,) + od
+        y = torch.empty(shape, dtype=torch.float32, device=x.device)
+        lib = kernels_lib()
+        need = lib.rt_conv3d_workspace_size(self._plan, n)
+        if need and (self._ws is None or self._ws.numel() < need):
+            self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        _check(lib.rt_conv3d_enqueue(self._plan, n, _p(x), _p(skip), _p(y), _p(self._ws) if need else None, _stream()),
+               "rt_conv3d_enqueue")
+        return y
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None):
+                kernels_lib().rt_conv3d_destroy(self._plan)
+        except Exception:
+            pass
+
+
+class Conv2d:
+    """IConvolutionLayer / IDeconvolutionLayer plan: x [N,Cin,H,W] -> y [N,Cout,Ho,Wo]."""
+
+    def __init__(self, weights, bias, stride, pad, in_hw, transposed=False, fuse_elu=False):
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+        d = Conv2dDesc()
+        d.transposed = int(transposed)
+        if transposed:
+            d.cin, d.cout = w.shape[0], w.shape[1]
+        else:
+            d.cout, d.cin = w.shape[0], w.shape[1]
+        d.r, d.s = w.shape[2], w.shape[3]
+        d.stride[:] = list(stride)
+        d.pad[:] = list(pad)
+        d.in_h, d.in_w = in_hw
+        d.weights_dtype = RT_F32
+        d.weights = w.ctypes.data
+        d.bias = b.ctypes.data if b is not None else None
+        d.fuse_elu = int(fuse_elu)
+        self.desc = d
+        self._plan = C.c_void_p()
+        rc = kernels_lib().rt_conv2d_create(C.byref(d), C.byref(self._plan))
+        if rc != 0:
+            raise RedtailError("rt_conv2d_create failed with status %d" % rc)
+        oh, ow = C.c_int(), C.c_int()
+        kernels_lib().rt_conv2d_out_dims(self._plan, C.byref(oh), C.byref(ow))
+        self.out_hw = (oh.value, ow.value)
+
+    def __call__(self, x):
+        _dev(x)
+        n = x.shape[0]
+        y = torch.empty((n, self.desc.cout) + self.out_hw, dtype=torch.float32, device=x.device)
+        _check(kernels_lib().rt_conv2d_enqueue(self._plan, n, _p(x), _p(y), _stream()), "rt_conv2d_enqueue")
+        return y
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None):
+                kernels_lib().rt_conv2d_destroy(self._plan)
+        except Exception:
+            pass
+
+
+def launch_count():
+    return int(kernels_lib().rt_launch_count())
+
+
+def last_kernel():
+    return kernels_lib().rt_last_kernel().decode()

@@ -1,0 +1,26 @@
+#!/bin/bash
+# Drop-in proof: compiles the UNCHANGED reference sources -- the gtest suite stereoDNN/tests/tests_main.cpp and the four
+# generated network builders stereoDNN/sample_app/*_net.cpp -- where they lie under /root/reference, against this repo's
+# headers (include/NvInfer.h, redtail_tensorrt_plugins.h, internal_utils.h) and links them to libnvstereo_inference.so.
+# Outputs go to dropin/_ref/ (git-ignored, travels to the GPU box like the other built binaries).  Only runs where
+# /root/reference exists; nothing is copied from it.
+set -e
+ROOT="$(cd "$(dirname "$0")/../.." && pwd)"
+REF=/root/reference/stereoDNN
+[ -d "$REF" ] || { echo "no reference checkout at $REF: skipping drop-in build"; exit 0; }
+OUT="$ROOT/dropin/_ref"
+mkdir -p "$OUT"
+INC="-I$ROOT/include -I$ROOT/tools/dropin/include -I/usr/local/cuda/include"
+LIB="-L$ROOT/redtail_b200/lib -lnvstereo_inference -lredtail_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,\$ORIGIN/../../redtail_b200/lib"
+CXX="${CXX:-g++} -std=c++14 -O1 -w"
+for n in nvsmall_1025x321 nvtiny_513x161 resnet18_1025x321 resnet18_2D_513x257; do
+  $CXX $INC -c "$REF/sample_app/${n}_net.cpp" -o "$OUT/${n}_net.o"
+done
+$CXX $INC -c "$REF/tests/tests_main.cpp" -o "$OUT/tests_main.o"
+$CXX $INC -c "$ROOT/tools/dropin/gtest_lite.cpp" -o "$OUT/gtest_lite.o"
+$CXX -o "$OUT/nvstereo_tests" "$OUT/tests_main.o" "$OUT/gtest_lite.o" $LIB
+# The builders are linked into a small driver (tools/dropin/net_driver.cpp) that calls create<Net>Network() exactly like
+# sample_app/main.cpp does and runs the engine on raw .bin images.
+$CXX $INC -I"$REF/sample_app" -c "$ROOT/tools/dropin/net_driver.cpp" -o "$OUT/net_driver.o"
+$CXX -o "$OUT/nvstereo_net_driver" "$OUT/net_driver.o" "$OUT"/*_net.o $LIB
+echo "built: $OUT/nvstereo_tests $OUT/nvstereo_net_driver"

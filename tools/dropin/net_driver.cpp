@@ -1,0 +1,108 @@
+// Drives the reference's UNCHANGED generated network builders (stereoDNN/sample_app/*_net.cpp, declared in the
+// reference's networks.h) through this repo's nvinfer1-compatible engine: the same call sequence as
+// sample_app/main.cpp:176-315 minus OpenCV (raw CHW float32 .bin images in, raw float32 disparity out).
+// Test infrastructure (tools/dropin); built only where /root/reference exists.
+//
+//   nvstereo_net_driver <nvsmall|nvtiny|resnet18|resnet18_2D> <width> <height> <weights.bin> <left.bin> <right.bin> <out.bin> [profile]
+#include <NvInfer.h>
+#include <cuda_runtime_api.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "redtail_tensorrt_plugins.h"
+#include "networks.h"
+
+using namespace nvinfer1;
+using namespace redtail::tensorrt;
+
+struct Log : public ILogger {
+    void log(Severity s, const char* msg) override { if (s <= Severity::kWARNING) std::cerr << "TRT: " << msg << std::endl; }
+};
+struct Prof : public IProfiler {
+    void reportLayerTime(const char* n, float ms) override { printf("%-64.64s %8.3f ms\n", n, ms); total += ms; }
+    float total = 0;
+};
+
+static std::vector<float> readBin(const char* path)
+{
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) { fprintf(stderr, "cannot open %s\n", path); exit(2); }
+    const size_t n = f.tellg();
+    f.seekg(0);
+    std::vector<float> v(n / 4);
+    f.read(reinterpret_cast<char*>(v.data()), n);
+    return v;
+}
+
+static std::unordered_map<std::string, Weights> readWeights(const char* path, std::vector<std::vector<float>>& keep)
+{
+    std::unordered_map<std::string, Weights> w;
+    std::ifstream f(path, std::ios::binary);
+    if (!f) { fprintf(stderr, "cannot open %s\n", path); exit(2); }
+    while (f.peek() != std::ifstream::traits_type::eof()) {
+        std::string name;
+        std::getline(f, name, '\0');
+        uint32_t count = 0;
+        f.read(reinterpret_cast<char*>(&count), 4);
+        keep.emplace_back(count);
+        f.read(reinterpret_cast<char*>(keep.back().data()), count * 4ull);
+        w[name] = Weights{DataType::kFLOAT, keep.back().data(), count};
+    }
+    return w;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 8) { fprintf(stderr, "usage: %s model w h weights left.bin right.bin out.bin [profile]\n", argv[0]); return 1; }
+    const std::string model = argv[1];
+    const int w = atoi(argv[2]), h = atoi(argv[3]);
+    Log log;
+    std::vector<std::vector<float>> keep;
+    auto weights = readWeights(argv[4], keep);
+    auto left = readBin(argv[5]), right = readBin(argv[6]);
+    if (left.size() != size_t(3) * h * w || right.size() != left.size()) { fprintf(stderr, "image size mismatch\n"); return 2; }
+
+    auto container = IPluginContainer::create(log);
+    IBuilder* builder = createInferBuilder(log);
+    INetworkDefinition* net = nullptr;
+    if (model == "nvsmall") net = createNVSmall1025x321Network(*builder, *container, DimsCHW{3, h, w}, weights, DataType::kFLOAT, log);
+    else if (model == "nvtiny") net = createNVTiny513x161Network(*builder, *container, DimsCHW{3, h, w}, weights, DataType::kFLOAT, log);
+    else if (model == "resnet18") net = createResNet18_1025x321Network(*builder, *container, DimsCHW{3, h, w}, weights, DataType::kFLOAT, log);
+    else if (model == "resnet18_2D") net = createResNet18_2D_513x257Network(*builder, *container, DimsCHW{3, h, w}, weights, DataType::kFLOAT, log);
+    else { fprintf(stderr, "unknown model\n"); return 1; }
+    builder->setMaxBatchSize(1);
+    builder->setMaxWorkspaceSize(size_t(1) << 30);
+    ICudaEngine* engine = builder->buildCudaEngine(*net);
+    net->destroy();
+    builder->destroy();
+    if (!engine) { fprintf(stderr, "engine build failed\n"); return 3; }
+    if (engine->getNbBindings() != 3) { fprintf(stderr, "expected 3 bindings\n"); return 3; }
+    void* buf[3];
+    const int il = engine->getBindingIndex("left"), ir = engine->getBindingIndex("right"), io = engine->getBindingIndex("disp");
+    std::vector<float> out(size_t(h) * w);
+    cudaMalloc(&buf[il], left.size() * 4); cudaMalloc(&buf[ir], right.size() * 4); cudaMalloc(&buf[io], out.size() * 4);
+    cudaMemcpy(buf[il], left.data(), left.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(buf[ir], right.data(), right.size() * 4, cudaMemcpyHostToDevice);
+    IExecutionContext* ctx = engine->createExecutionContext();
+    Prof prof;
+    if (argc > 8) ctx->setProfiler(&prof);
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    const bool ok = ctx->execute(1, buf);
+    const auto t1 = std::chrono::high_resolution_clock::now();
+    if (!ok) { fprintf(stderr, "execute failed\n"); return 4; }
+    printf("Host time: %.3f ms (%d engine steps)\n", std::chrono::duration<float, std::milli>(t1 - t0).count(), engine->getNbLayers());
+    if (argc > 8) printf("All layers: %.3f ms\n", prof.total);
+    cudaMemcpy(out.data(), buf[io], out.size() * 4, cudaMemcpyDeviceToHost);
+    std::ofstream(argv[7], std::ios::binary).write(reinterpret_cast<const char*>(out.data()), out.size() * 4);
+    ctx->destroy();
+    engine->destroy();
+    for (auto b : buf) cudaFree(b);
+    return 0;
+}
