@@ -50,7 +50,7 @@ def synthetic_pairs(batch, seed=1234):
         x1 = np.minimum(x0 + 1, W - 1)
         a = (xs - x0).astype(np.float32)
         rows = np.arange(H)[:, None]
-        right = ((1 - a) * left[:, rows, x0] + a * left[:, rows, x1]).astype(np.float32)
+        right = np.ascontiguousarray((1 - a) * left[:, rows, x0] + a * left[:, rows, x1], dtype=np.float32)
         ls.append(left)
         rs.append(right)
     return np.stack(ls), np.stack(rs)

@@ -93,4 +93,4 @@ def synthetic_pair(h, w, seed=1234):
     a = (xs - x0).astype(np.float32)
     rows = np.arange(h)[:, None]
     right = (1 - a) * left[:, rows, x0] + a * left[:, rows, x1]
-    return left, right.astype(np.float32)
+    return left, np.ascontiguousarray(right, dtype=np.float32)

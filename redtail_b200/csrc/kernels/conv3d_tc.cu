@@ -1,9 +1,521 @@
-// placeholder, replaced by the tcgen05 implementation
+// 3-D convolution / transposed convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM,
+// operands staged by TMA) -- the one dense contraction of the stereo nets (98.9 % of NVSmall's FLOPs).
+//
+// Replaces cudnnConvolutionForward + cudnnAddTensor (lib/conv3d_plugin.cpp:204-210) and
+// cudnnConvolutionBackwardData + addDBiasTo3DConv (lib/conv3d_transpose_plugin.cpp:223-237), plus -- fused in the
+// epilogue -- the Transform, Slice, skip-add and ELU passes that follow them in the generated builders.
+//
+// Formulation: implicit GEMM, one output tile = 128 output positions (a th x tw patch of one output depth plane)
+// x Cout channels.  GEMM-M = positions, GEMM-N = Cout, GEMM-K = taps x Cin, walked one (tap, 64-channel block) at a
+// time.  Activations are first re-laid out channels-last as fp16 ([N][D][H][W][C], see pack kernel) so that the A
+// operand of a tap is a plain TMA box [tw x th x KC] at a shifted coordinate -- zero padding (D, H and W) is TMA
+// out-of-bounds fill, never materialised; stride-2 convolutions use TMA traversal strides.  A transposed convolution
+// of stride s is s^3 independent "parity classes", each a stride-1 convolution over a subset of the taps whose
+// outputs are scattered with stride s by the epilogue.
+//
+// Numerics (RT_PREC_FP32): the fp32 tolerance of the plugin path (1e-3 px disparity after 11 chained layers) cannot be
+// held by a single fp16/bf16/tf32 product.  Every operand x is split as x = hi + 2^-11 * lo with hi = fp16(x),
+// lo = fp16((x - hi) * 2^11) -- 22 significant bits -- and the kernel accumulates the three leading products in fp32
+// TMEM:  D0 += A_hi * W_hi ;  D1 += A_hi * W_lo + A_lo * W_hi ;  result = D0 + 2^-11 * D1  (dropped term ~2^-22).
+// The first two products share one MMA of N = 2*Cout ([W_hi ; W_lo] stacked along N), so A_hi is read once.
+// RT_PREC_FP16 issues only the hi*hi product (the reference's fp16 configs, 1e-2 tolerance).
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 epilogue (TMEM -> registers ->
+// bias / skip / ELU -> coalesced fp32 stores).  Persistent grid (one CTA per SM), static round-robin tile schedule,
+// smem ring of kStages operand stages, two TMEM accumulator buffers so the epilogue of tile i overlaps the MMAs of i+1.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
 #include "common.cuh"
 #include "conv3d_internal.h"
+#include "tma.cuh"
+
 namespace rt {
-int tc_plan_init(rt_conv3d_plan*, const std::vector<float>&, const std::vector<float>&) { return RT_ERR_UNSUPPORTED; }
-void tc_plan_destroy(rt_conv3d_plan*) {}
-size_t tc_workspace_size(const rt_conv3d_plan*, int) { return 0; }
-int tc_conv3d_enqueue(const rt_conv3d_plan*, int, const float*, const float*, float*, void*, cudaStream_t) { return RT_ERR_UNSUPPORTED; }
+namespace {
+
+constexpr int kMaxTaps = 27;
+constexpr int kMaxClasses = 8;
+constexpr int kThreads = 192;
+constexpr int kTileM = 128;
+
+struct TapEntry { int8_t dd, dh, dw; uint8_t widx; };     // A-coordinate offsets, weight tap index
+
+struct ClassInfo {
+    int ntaps;
+    int ed, eh, ew;          // output offset within the stride-s lattice (0 for forward conv)
+    int dc, hc, wc;          // class-local output extent
+    int tiles_h, tiles_w;
+    int job_begin;           // first job index of this class (per sample)
+    TapEntry taps[kMaxTaps];
+};
+
+struct TcParams {
+    int nclasses;
+    int jobs_per_sample, njobs;
+    int in_s[3];             // A coordinate = idx * in_s + tap offset   (conv stride, 1 for transposed)
+    int out_s[3];            // output position = idx * out_s + e        (1 for conv, stride for transposed)
+    int th, tw;
+    int kc, ncb;             // channels per K block, K blocks per tap
+    int cout, nb;            // real output channels, GEMM-N of the B tile (2*cout_pad in fp32 mode)
+    int cout_pad;
+    int split;               // 1: hi/lo operands (RT_PREC_FP32), 0: hi only
+    int stages;
+    int a_bytes, b_bytes, stage_bytes;
+    int out_d, out_h, out_w; // output extent actually written
+    long long out_sn, out_sc, out_sd;   // element strides of sample, channel, depth in the dense fp32 output
+    int fuse_elu;
+    ClassInfo cls[kMaxClasses];
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Pack: dense fp32 [n][..] with arbitrary (d, c) strides -> channels-last fp16 hi (and lo) [n][D][H][W][C].
+// One CTA handles 64 consecutive w of one (n, d, h) row for all C channels through a padded smem transpose.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int d_ext, int c_ext,
+                  int h_ext, int w_ext, long long s_n, long long s_d, long long s_c) {
+    extern __shared__ float tile[];                    // [c_ext][65]
+    const int w0 = blockIdx.x * 64;
+    const int h = blockIdx.y;
+    const int d = blockIdx.z % d_ext, n = blockIdx.z / d_ext;
+    const float* src = x + n * s_n + d * s_d + static_cast<long long>(h) * w_ext;
+    for (int i = threadIdx.x; i < c_ext * 64; i += 256) {
+        const int c = i >> 6, w = i & 63;
+        tile[c * 65 + w] = (w0 + w < w_ext) ? __ldg(src + c * s_c + w0 + w) : 0.f;
+    }
+    __syncthreads();
+    const long long pix0 = ((static_cast<long long>(n) * d_ext + d) * h_ext + h) * w_ext + w0;
+    const int groups = c_ext >> 3;                     // 8 channels (16 bytes of fp16) per thread-item
+    for (int i = threadIdx.x; i < 64 * groups; i += 256) {
+        const int w = i / groups, g = i % groups;
+        if (w0 + w >= w_ext) continue;
+        __align__(16) __half hv[8];
+        __align__(16) __half lv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float v = tile[(g * 8 + k) * 65 + w];
+            v = fminf(fmaxf(v, -65504.f), 65504.f);    // fp16 range (documented limit of the split scheme)
+            const __half hh = __float2half_rn(v);
+            hv[k] = hh;
+            lv[k] = __float2half_rn((v - __half2float(hh)) * 2048.f);
+        }
+        const long long o = (pix0 + w) * c_ext + g * 8;
+        *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(hv);
+        if (lo) *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(lv);
+    }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Main kernel.
+// ---------------------------------------------------------------------------------------------------------------
+struct JobCoord { int cls, n, d, h0, w0; };
+
+__device__ __forceinline__ JobCoord decode_job(const TcParams& p, int job) {
+    JobCoord j;
+    j.n = job / p.jobs_per_sample;
+    int r = job - j.n * p.jobs_per_sample;
+    int c = 0;
+    while (c + 1 < p.nclasses && r >= p.cls[c + 1].job_begin) ++c;
+    j.cls = c;
+    r -= p.cls[c].job_begin;
+    const int tw_n = p.cls[c].tiles_w, th_n = p.cls[c].tiles_h;
+    j.w0 = (r % tw_n) * p.tw;
+    r /= tw_n;
+    j.h0 = (r % th_n) * p.th;
+    j.d = r / th_n;
+    return j;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ TcParams p,
+                   const float* __restrict__ bias, const float* __restrict__ skip, float* __restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // Carve: [stages x stage_bytes] operand ring (1024-aligned) | barriers | tmem address | bias
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* ring = smem;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(p.stages) * p.stage_bytes);
+    uint64_t* empty_bar = full_bar + 8;
+    uint64_t* tmem_full = empty_bar + 8;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_addr_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_bias = reinterpret_cast<float*>(tmem_addr_slot + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        prefetch_tensormap(&map_a_hi);
+        if (p.split) prefetch_tensormap(&map_a_lo);
+        prefetch_tensormap(&map_w);
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < p.cout_pad; i += kThreads) s_bias[i] = i < p.cout ? bias[i] : 0.f;
+    if (warp == 1) tmem_alloc<512>(tmem_addr_slot);      // one CTA per SM: take the whole TMEM (2 accumulator buffers)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_addr_slot;
+    const int acc_cols = p.nb;                            // columns per accumulator buffer (<= 256)
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
+                const JobCoord jc = decode_job(p, job);
+                const ClassInfo& ci = p.cls[jc.cls];
+                for (int t = 0; t < ci.ntaps; ++t) {
+                    const TapEntry te = ci.taps[t];
+                    const int cw = jc.w0 * p.in_s[2] + te.dw;
+                    const int chh = jc.h0 * p.in_s[1] + te.dh;
+                    const int cd = jc.d * p.in_s[0] + te.dd;
+                    for (int cb = 0; cb < p.ncb; ++cb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* st = ring + static_cast<size_t>(stage) * p.stage_bytes;
+                        mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes * (p.split ? 2 : 1) + p.b_bytes);
+                        tma_load_5d(st, &map_a_hi, &full_bar[stage], cb * p.kc, cw, chh, cd, jc.n);
+                        if (p.split) tma_load_5d(st + p.a_bytes, &map_a_lo, &full_bar[stage], cb * p.kc, cw, chh, cd, jc.n);
+                        tma_load_2d(st + p.a_bytes * (p.split ? 2 : 1), &map_w, &full_bar[stage], 0,
+                                    (static_cast<int>(te.widx) * p.ncb + cb) * p.nb);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t pitch = p.kc * 2;                                   // bytes per operand row = swizzle span
+            const uint32_t swz = p.kc == 64 ? 2u : (p.kc == 32 ? 4u : 6u);     // SWIZZLE_128B / 64B / 32B
+            const uint32_t idesc_full = umma_idesc_f16(kTileM, p.nb);
+            const uint32_t idesc_half = umma_idesc_f16(kTileM, p.cout_pad);
+            int stage = 0;
+            uint32_t phase = 0;
+            int buf = 0;
+            uint32_t buf_phase[2] = {0, 0};
+            for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
+                const JobCoord jc = decode_job(p, job);
+                const int nkb = p.cls[jc.cls].ntaps * p.ncb;
+                mbar_wait(&tmem_empty[buf], buf_phase[buf] ^ 1);               // epilogue drained this buffer
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + static_cast<uint32_t>(buf * acc_cols);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(ring + static_cast<size_t>(stage) * p.stage_bytes);
+                    const uint32_t a_lo = a_hi + p.a_bytes;
+                    const uint32_t b = a_hi + p.a_bytes * (p.split ? 2 : 1);
+                    for (int kk = 0; kk < p.kc / 16; ++kk) {
+                        const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
+                        const uint64_t da = umma_smem_desc(a_hi + kk * 32, pitch, swz, 0);
+                        const uint64_t db = umma_smem_desc(b + kk * 32, pitch, swz, 0);
+                        umma_f16(d0, da, db, idesc_full, acc);                 // [A_hi*W_hi | A_hi*W_lo]
+                        if (p.split) {
+                            const uint64_t dl = umma_smem_desc(a_lo + kk * 32, pitch, swz, 0);
+                            umma_f16(d0 + p.cout_pad, dl, db, idesc_half, 1u); // += A_lo*W_hi into the cross-term columns
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);                            // slot free once these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[buf]);                                  // accumulator complete
+                buf_phase[buf] ^= 1;
+                buf ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;                     // tile row = output position within the patch
+        const int hl = m / p.tw, wl = m % p.tw;
+        int buf = 0;
+        uint32_t buf_phase[2] = {0, 0};
+        for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
+            const JobCoord jc = decode_job(p, job);
+            const ClassInfo& ci = p.cls[jc.cls];
+            mbar_wait(&tmem_full[buf], buf_phase[buf]);
+            tc_fence_after();
+            const int hi_ = jc.h0 + hl, wi_ = jc.w0 + wl;
+            const bool valid = hi_ < ci.hc && wi_ < ci.wc;
+            const int od = jc.d * p.out_s[0] + ci.ed, oh = hi_ * p.out_s[1] + ci.eh, ow = wi_ * p.out_s[2] + ci.ew;
+            const long long obase = jc.n * p.out_sn + od * p.out_sd + static_cast<long long>(oh) * p.out_w + ow;
+            const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * acc_cols);
+            for (int c0 = 0; c0 < p.cout_pad; c0 += 16) {
+                uint32_t v0[16], v1[16];
+                tmem_ld16(trow + c0, v0);
+                if (p.split) tmem_ld16(trow + p.cout_pad + c0, v1);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const int c = c0 + k;
+                        if (c < p.cout) {
+                            float val = __uint_as_float(v0[k]);
+                            if (p.split) val = fmaf(__uint_as_float(v1[k]), 1.f / 2048.f, val);
+                            val += s_bias[c];
+                            const long long idx = obase + c * p.out_sc;
+                            if (skip) val += __ldg(skip + idx);
+                            if (p.fuse_elu) val = elu1(val);
+                            out[idx] = val;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            buf_phase[buf] ^= 1;
+            buf ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host side.
+// ---------------------------------------------------------------------------------------------------------------
+struct TcPlan {
+    TcParams p{};
+    __half* w_dev = nullptr;          // packed weights [taps][ncb][nb][kc]
+    CUtensorMap map_w{};
+    int cin = 0;
+    int in_d = 0, in_h = 0, in_w = 0; // input spatial extent
+    long long in_sn = 0, in_sd = 0, in_sc = 0;   // dense fp32 input strides (sample, depth, channel)
+    size_t in_elems = 0;              // per sample, = D*H*W*C
+    int smem_bytes = 0;
+};
+
+uint16_t f2h_bits(float f) {
+    __half h = __float2half_rn(f);
+    uint16_t b;
+    memcpy(&b, &h, 2);
+    return b;
+}
+float h2f_bits(uint16_t b) {
+    __half h;
+    memcpy(&h, &b, 2);
+    return __half2float(h);
+}
+
+}  // namespace
+
+int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::vector<float>& /*bias*/) {
+    const rt_conv3d_desc& d = plan->desc;
+    const bool tr = d.transposed != 0;
+    const int cin = plan->cin, cout = plan->cout;
+    // Coverage of the tensor-core tiles.
+    if (cin % 16 != 0 || cin < 16) return RT_ERR_UNSUPPORTED;
+    if (cin > 64 && cin % 64 != 0) return RT_ERR_UNSUPPORTED;
+    if (cin < 64 && cin != 16 && cin != 32) return RT_ERR_UNSUPPORTED;
+    const int cout_pad = (cout + 15) / 16 * 16;
+    const bool split = d.precision == RT_PREC_FP32;
+    const int nb = split ? 2 * cout_pad : cout_pad;
+    if (nb > 256) return RT_ERR_UNSUPPORTED;
+    if (d.v > 3 || d.r > 3 || d.s > 3) return RT_ERR_UNSUPPORTED;
+    for (int i = 0; i < 3; ++i)
+        if (d.stride[i] > 2) return RT_ERR_UNSUPPORTED;
+    if (!get_encode_tiled()) return RT_ERR_UNSUPPORTED;
+
+    TcPlan* t = new TcPlan();
+    TcParams& p = t->p;
+    t->cin = cin;
+    p.split = split;
+    p.kc = cin >= 64 ? 64 : cin;
+    p.ncb = cin / p.kc;
+    p.cout = cout; p.cout_pad = cout_pad; p.nb = nb;
+    p.fuse_elu = d.fuse_elu;
+    const int kdim[3] = {d.v, d.r, d.s};
+    int out_ext[3];
+    if (!tr) {
+        t->in_d = d.in_dims[0]; t->in_h = d.in_dims[2]; t->in_w = d.in_dims[3];
+        t->in_sd = static_cast<long long>(cin) * t->in_h * t->in_w;      // input [D,C,H,W]
+        t->in_sc = static_cast<long long>(t->in_h) * t->in_w;
+        out_ext[0] = d.out_dims[1]; out_ext[1] = d.out_dims[2]; out_ext[2] = d.out_dims[3];
+        for (int i = 0; i < 3; ++i) { p.in_s[i] = d.stride[i]; p.out_s[i] = 1; }
+        const long long plane = static_cast<long long>(out_ext[1]) * out_ext[2];
+        if (d.out_transposed) { p.out_sd = cout * plane; p.out_sc = plane; }          // [Do,K,Ho,Wo]
+        else { p.out_sc = out_ext[0] * plane; p.out_sd = plane; }                       // [K,Do,Ho,Wo]
+        p.out_sn = static_cast<long long>(cout) * out_ext[0] * plane;
+    } else {
+        t->in_d = d.in_dims[1]; t->in_h = d.in_dims[2]; t->in_w = d.in_dims[3];
+        t->in_sc = static_cast<long long>(t->in_d) * t->in_h * t->in_w;  // input [K,D,H,W]
+        t->in_sd = static_cast<long long>(t->in_h) * t->in_w;
+        out_ext[0] = plan->out_planes; out_ext[1] = d.out_dims[2]; out_ext[2] = d.out_dims[3];
+        for (int i = 0; i < 3; ++i) { p.in_s[i] = 1; p.out_s[i] = d.stride[i]; }
+        const long long plane = static_cast<long long>(out_ext[1]) * out_ext[2];
+        p.out_sd = cout * plane; p.out_sc = plane;                                      // [Dx,C,Hx,Wx]
+        p.out_sn = static_cast<long long>(out_ext[0]) * cout * plane;
+    }
+    t->in_sn = static_cast<long long>(cin) * t->in_d * t->in_h * t->in_w;
+    t->in_elems = static_cast<size_t>(t->in_sn);
+    p.out_d = out_ext[0]; p.out_h = out_ext[1]; p.out_w = out_ext[2];
+
+    // Parity classes and their tap tables.
+    int ncls[3];
+    for (int i = 0; i < 3; ++i) ncls[i] = tr ? d.stride[i] : 1;
+    p.nclasses = ncls[0] * ncls[1] * ncls[2];
+    // Patch shape: minimise padded area over the class-local extents (use the largest class = class 0).
+    const int cls_h = tr ? (out_ext[1] + d.stride[1] - 1) / d.stride[1] : out_ext[1];
+    const int cls_w = tr ? (out_ext[2] + d.stride[2] - 1) / d.stride[2] : out_ext[2];
+    long long best = -1;
+    for (int tw = 8; tw <= 128; tw *= 2) {
+        const int th = kTileM / tw;
+        if (!tr && (tw * d.stride[2] > 256 || th * d.stride[1] > 256)) continue;       // TMA box limit
+        const long long area = static_cast<long long>((cls_w + tw - 1) / tw) * tw * ((cls_h + th - 1) / th) * th;
+        if (best < 0 || area < best) { best = area; p.tw = tw; p.th = th; }
+    }
+    int job = 0, ci = 0;
+    for (int ed = 0; ed < ncls[0]; ++ed)
+        for (int eh = 0; eh < ncls[1]; ++eh)
+            for (int ew = 0; ew < ncls[2]; ++ew, ++ci) {
+                ClassInfo& c = p.cls[ci];
+                c.ed = ed; c.eh = eh; c.ew = ew;
+                const int e[3] = {ed, eh, ew};
+                int ext[3];
+                for (int i = 0; i < 3; ++i) ext[i] = tr ? (out_ext[i] - e[i] + d.stride[i] - 1) / d.stride[i] : out_ext[i];
+                c.dc = ext[0] > 0 ? ext[0] : 0; c.hc = ext[1] > 0 ? ext[1] : 0; c.wc = ext[2] > 0 ? ext[2] : 0;
+                c.tiles_h = (c.hc + p.th - 1) / p.th; c.tiles_w = (c.wc + p.tw - 1) / p.tw;
+                c.job_begin = job;
+                job += c.dc * c.tiles_h * c.tiles_w;
+                c.ntaps = 0;
+                for (int v = 0; v < d.v; ++v)
+                    for (int r = 0; r < d.r; ++r)
+                        for (int s = 0; s < d.s; ++s) {
+                            const int tap[3] = {v, r, s};
+                            int off[3];
+                            bool ok = true;
+                            for (int i = 0; i < 3; ++i) {
+                                if (!tr) off[i] = tap[i] - d.pad[i];
+                                else {
+                                    const int num = e[i] + d.pad[i] - tap[i];
+                                    // floor-mod so that negative numerators classify correctly
+                                    if (((num % d.stride[i]) + d.stride[i]) % d.stride[i] != 0) { ok = false; break; }
+                                    off[i] = num >= 0 ? num / d.stride[i] : -((-num) / d.stride[i]);
+                                }
+                            }
+                            if (!ok) continue;
+                            TapEntry te;
+                            te.dd = static_cast<int8_t>(off[0]); te.dh = static_cast<int8_t>(off[1]); te.dw = static_cast<int8_t>(off[2]);
+                            te.widx = static_cast<uint8_t>((v * d.r + r) * d.s + s);
+                            c.taps[c.ntaps++] = te;
+                        }
+            }
+    p.jobs_per_sample = job;
+
+    // Weight packing: [tap][cb][row][kc] fp16; rows 0..cout_pad-1 = hi, rows cout_pad.. = lo (fp32 mode).
+    const int ntap = d.v * d.r * d.s;
+    std::vector<uint16_t> pk(static_cast<size_t>(ntap) * p.ncb * nb * p.kc, 0);
+    for (int k = 0; k < d.k; ++k)
+        for (int v = 0; v < d.v; ++v)
+            for (int c = 0; c < d.c; ++c)
+                for (int r = 0; r < d.r; ++r)
+                    for (int s = 0; s < d.s; ++s) {
+                        float val = w[(((static_cast<size_t>(k) * d.v + v) * d.c + c) * d.r + r) * d.s + s];
+                        val = val > 65504.f ? 65504.f : (val < -65504.f ? -65504.f : val);
+                        const int co = tr ? c : k, ci2 = tr ? k : c;
+                        const int tap = (v * d.r + r) * d.s + s;
+                        const size_t base = ((static_cast<size_t>(tap) * p.ncb + ci2 / p.kc) * nb) * p.kc + (ci2 % p.kc);
+                        const uint16_t hb = f2h_bits(val);
+                        pk[base + static_cast<size_t>(co) * p.kc] = hb;
+                        if (split) pk[base + static_cast<size_t>(cout_pad + co) * p.kc] = f2h_bits((val - h2f_bits(hb)) * 2048.f);
+                    }
+    if (cudaMalloc(&t->w_dev, pk.size() * 2) != cudaSuccess ||
+        cudaMemcpy(t->w_dev, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(t->w_dev);
+        delete t;
+        return static_cast<int>(cudaErrorMemoryAllocation);
+    }
+    const CUtensorMapSwizzle swz = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    {
+        const uint64_t dims[2] = {static_cast<uint64_t>(p.kc), static_cast<uint64_t>(ntap) * p.ncb * nb};
+        const uint64_t strides[1] = {static_cast<uint64_t>(p.kc) * 2};
+        const uint32_t box[2] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(nb)};
+        const int rc = make_tensor_map(&t->map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, t->w_dev, dims, strides, box, nullptr, swz);
+        if (rc != 0) { cudaFree(t->w_dev); delete t; return rc > 0 ? rc : RT_ERR_UNSUPPORTED; }
+    }
+    // Shared-memory budget.
+    p.a_bytes = kTileM * p.kc * 2;
+    p.b_bytes = (nb * p.kc * 2 + 1023) & ~1023;
+    p.stage_bytes = p.a_bytes * (split ? 2 : 1) + p.b_bytes;
+    p.stages = (196 * 1024) / p.stage_bytes;
+    if (p.stages > 8) p.stages = 8;
+    if (p.stages < 2) { cudaFree(t->w_dev); delete t; return RT_ERR_UNSUPPORTED; }
+    t->smem_bytes = p.stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + cout_pad * 4;
+    plan->tc = t;
+    return RT_OK;
+}
+
+void tc_plan_destroy(rt_conv3d_plan* plan) {
+    TcPlan* t = static_cast<TcPlan*>(plan->tc);
+    if (!t) return;
+    cudaFree(t->w_dev);
+    delete t;
+    plan->tc = nullptr;
+}
+
+size_t tc_workspace_size(const rt_conv3d_plan* plan, int max_batch) {
+    const TcPlan* t = static_cast<const TcPlan*>(plan->tc);
+    const size_t per = (t->in_elems * 2 + 255) & ~static_cast<size_t>(255);
+    return per * (t->p.split ? 2 : 1) * static_cast<size_t>(max_batch) + 256;
+}
+
+int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const float* skip, float* y, void* workspace,
+                      cudaStream_t s) {
+    const TcPlan* t = static_cast<const TcPlan*>(plan->tc);
+    if (!workspace) return RT_ERR_ARG;
+    TcParams p = t->p;
+    p.njobs = p.jobs_per_sample * n;
+    if (p.njobs == 0) return RT_OK;
+    const size_t per = (t->in_elems * 2 + 255) & ~static_cast<size_t>(255);
+    __half* hi = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
+    __half* lo = p.split ? reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(hi) + per * n) : nullptr;
+    // When n > 1 the per-sample blocks must be contiguous for the 5-D tensor map: per == in_elems*2 unless padded.
+    if (n > 1 && per != t->in_elems * 2) return RT_ERR_UNSUPPORTED;
+
+    // 1. pack
+    {
+        if (static_cast<long long>(n) * t->in_d > 65535 || t->in_h > 65535) return RT_ERR_UNSUPPORTED;
+        dim3 grid((t->in_w + 63) / 64, t->in_h, n * t->in_d);
+        const size_t sm = static_cast<size_t>(t->cin) * 65 * sizeof(float);
+        pack_split_kernel<<<grid, 256, sm, s>>>(x, hi, lo, t->in_d, t->cin, t->in_h, t->in_w, t->in_sn, t->in_sd, t->in_sc);
+        note_launch("conv3d_pack_split");
+        RT_CHECK_LAUNCH();
+    }
+    // 2. tensor maps over the packed activations: dims (C, W, H, D, N)
+    CUtensorMap ma_hi, ma_lo;
+    {
+        const uint64_t dims[5] = {static_cast<uint64_t>(t->cin), static_cast<uint64_t>(t->in_w), static_cast<uint64_t>(t->in_h),
+                                  static_cast<uint64_t>(t->in_d), static_cast<uint64_t>(n)};
+        const uint64_t st[4] = {static_cast<uint64_t>(t->cin) * 2, static_cast<uint64_t>(t->cin) * 2 * t->in_w,
+                                static_cast<uint64_t>(t->cin) * 2 * t->in_w * t->in_h,
+                                static_cast<uint64_t>(t->cin) * 2 * t->in_w * t->in_h * t->in_d};
+        const uint32_t box[5] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.tw * p.in_s[2]),
+                                 static_cast<uint32_t>(p.th * p.in_s[1]), 1u, 1u};
+        const uint32_t es[5] = {1u, static_cast<uint32_t>(p.in_s[2]), static_cast<uint32_t>(p.in_s[1]), 1u, 1u};
+        const CUtensorMapSwizzle swz = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+        int rc = make_tensor_map(&ma_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, hi, dims, st, box, es, swz);
+        if (rc == 0 && p.split) rc = make_tensor_map(&ma_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, lo, dims, st, box, es, swz);
+        if (rc != 0) return rc > 0 ? rc : RT_ERR_UNSUPPORTED;
+        if (!p.split) ma_lo = ma_hi;
+    }
+    // 3. main kernel
+    static bool attr_set = false;
+    if (!attr_set) {
+        RT_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    int grid = num_sms();
+    if (grid > p.njobs) grid = p.njobs;
+    conv3d_umma_kernel<<<grid, kThreads, t->smem_bytes, s>>>(ma_hi, ma_lo, t->map_w, p, plan->bias, skip, y);
+    note_launch(p.split ? "conv3d_umma_fp16x2split" : "conv3d_umma_fp16");
+    RT_CHECK_LAUNCH();
+    return RT_OK;
+}
+
+}  // namespace rt

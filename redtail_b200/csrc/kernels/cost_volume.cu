@@ -59,7 +59,10 @@ cost_volume_tma_kernel(const __grid_constant__ CUtensorMap map_left, const __gri
                        T* __restrict__ out, int c, int hw, int w, int disp) {
     constexpr int V = 16 / sizeof(T);                       // elements per 128-bit word
     constexpr int kIters = kTile / (kThreads * V);          // vector stores per thread per disparity
-    __shared__ __align__(1024) T stage[kHalo + kTile + V];  // + V: the realign window may read one word past the end
+    // TMA needs a 16-byte aligned global start address, so the staged window starts at the plane position rounded
+    // DOWN to a 16-byte boundary (a0 elements early) and is one box longer; + V: the realign window may read one
+    // 16-byte word past the last consumed element.
+    __shared__ __align__(1024) T stage[kHalo + kTile + kBox + V];
     __shared__ __align__(8) uint64_t bar;
 
     const int tid = threadIdx.x;
@@ -73,18 +76,22 @@ cost_volume_tma_kernel(const __grid_constant__ CUtensorMap map_left, const __gri
         mbar_init(&bar, 1);
         fence_barrier_init();
     }
-    if (tid < V) stage[kHalo + kTile + tid] = from_f32<T>(0.f);
+    if (tid < V) stage[kHalo + kTile + kBox + tid] = from_f32<T>(0.f);
     __syncthreads();
+    // Flat element coordinate of the first wanted element (plane position j0 - kHalo) and its 16-byte aligned floor.
+    const long long want = (static_cast<long long>(n) * c + ch) * hw + j0 - kHalo;
+    const long long start = want & ~static_cast<long long>(V - 1);
+    const int a0 = static_cast<int>(want - start);          // 0 .. V-1
     if (tid == 0) {
         const CUtensorMap* m = is_right ? &map_right : &map_left;
-        // Flat element coordinate of stage[0]; negative / past-the-end boxes are zero-filled by TMA.  Elements that
-        // belong to a neighbouring plane are never consumed (the x >= d mask removes exactly those).
-        const long long start = (static_cast<long long>(n) * c + ch) * hw + j0 - kHalo;
-        mbar_arrive_expect_tx(&bar, (kHalo + kTile) * sizeof(T));
+        // Negative / past-the-end boxes are zero-filled by TMA.  Elements that belong to a neighbouring plane are
+        // never consumed (the x >= d mask removes exactly those).
+        mbar_arrive_expect_tx(&bar, (kHalo + kTile + kBox) * sizeof(T));
 #pragma unroll 1
-        for (int b = 0; b < (kHalo + kTile) / kBox; ++b)
+        for (int b = 0; b < (kHalo + kTile + kBox) / kBox; ++b)
             tma_load_1d(stage + b * kBox, m, &bar, static_cast<int>(start + b * kBox));
     }
+    const int org = kHalo + a0;                              // stage index of plane element j0
 
     // Row position (x) of this thread's vector slots, before the per-plane head shift.
     int xg[kIters];
@@ -108,15 +115,15 @@ cost_volume_tma_kernel(const __grid_constant__ CUtensorMap map_left, const __gri
         // scalar head and tail
         if (tid < head) {
             const int x = xs;                                // (j0 + tid) % w
-            dst[tid] = (!is_right || x >= d) ? stage[kHalo + tid - shift] : zero;
+            dst[tid] = (!is_right || x >= d) ? stage[org + tid - shift] : zero;
         }
         if (tid < tail) {
             const int jj = head + nvec * V + tid;
             const int x = (j0 + jj) % w;
-            dst[jj] = (!is_right || x >= d) ? stage[kHalo + jj - shift] : zero;
+            dst[jj] = (!is_right || x >= d) ? stage[org + jj - shift] : zero;
         }
         // aligned body
-        const int sbase = kHalo + head - shift;              // stage index of body element 0 (>= 0)
+        const int sbase = org + head - shift;              // stage index of body element 0 (>= 0)
         const int mb = (sbase * static_cast<int>(sizeof(T))) & 15;
         const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(stage) +
                                                          ((sbase * static_cast<int>(sizeof(T))) & ~15));
