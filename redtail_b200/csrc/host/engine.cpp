@@ -448,7 +448,8 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
     if (!net.resolve()) return false;
     if (net.outputs_.empty()) return fail("network has no outputs");
 
-    static const bool fusion = [] { const char* e = getenv("REDTAIL_ENGINE_FUSION"); return !(e && e[0] == '0'); }();
+    const char* fusion_env = getenv("REDTAIL_ENGINE_FUSION");
+    const bool fusion = !(fusion_env && fusion_env[0] == '0');
 
     // Tensor table.
     slots_.resize(net.tensors_.size());

@@ -61,7 +61,7 @@ struct TcParams {
     int cout_pad;
     int split;               // 1: hi/lo operands (RT_PREC_FP32), 0: hi only
     int stages;
-    int a_bytes, b_bytes, stage_bytes;
+    int a_bytes, b_bytes, b_tx, stage_bytes;   // b_bytes: 1 KB-rounded slot, b_tx: bytes the weight TMA actually delivers
     int out_d, out_h, out_w; // output extent actually written
     long long out_sn, out_sc, out_sd;   // element strides of sample, channel, depth in the dense fp32 output
     int fuse_elu;
@@ -176,7 +176,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     for (int cb = 0; cb < p.ncb; ++cb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* st = ring + static_cast<size_t>(stage) * p.stage_bytes;
-                        mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes * (p.split ? 2 : 1) + p.b_bytes);
+                        mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes * (p.split ? 2 : 1) + p.b_tx);
                         tma_load_5d(st, &map_a_hi, &full_bar[stage], cb * p.kc, cw, chh, cd, jc.n);
                         if (p.split) tma_load_5d(st + p.a_bytes, &map_a_lo, &full_bar[stage], cb * p.kc, cw, chh, cd, jc.n);
                         tma_load_2d(st + p.a_bytes * (p.split ? 2 : 1), &map_w, &full_bar[stage], 0,
@@ -441,12 +441,14 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     }
     // Shared-memory budget.
     p.a_bytes = kTileM * p.kc * 2;
-    p.b_bytes = (nb * p.kc * 2 + 1023) & ~1023;
+    p.b_tx = nb * p.kc * 2;
+    p.b_bytes = (p.b_tx + 1023) & ~1023;
     p.stage_bytes = p.a_bytes * (split ? 2 : 1) + p.b_bytes;
     p.stages = (196 * 1024) / p.stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) { cudaFree(t->w_dev); delete t; return RT_ERR_UNSUPPORTED; }
     t->smem_bytes = p.stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + cout_pad * 4;
+    if (t->smem_bytes < 120 * 1024) t->smem_bytes = 120 * 1024;   // > half of the SM: one CTA per SM, so the 512-column TMEM grab never contends
     plan->tc = t;
     return RT_OK;
 }
