@@ -36,7 +36,8 @@ namespace {
 
 constexpr int kMaxTaps = 27;
 constexpr int kMaxClasses = 8;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // producer warp + MMA warp + epilogue warps
 constexpr int kTileM = 128;
 
 struct TapEntry { int8_t dd, dh, dw; uint8_t widx; };     // A-coordinate offsets, weight tap index
@@ -61,6 +62,7 @@ struct TcParams {
     int cout_pad;
     int split;               // 1: hi/lo operands (RT_PREC_FP32), 0: hi only
     int stages;
+    int chunk_kb;            // K blocks accumulated in TMEM before the epilogue adds them up in fp32 registers
     int a_bytes, b_bytes, b_tx, stage_bytes;   // b_bytes: 1 KB-rounded slot, b_tx: bytes the weight TMA actually delivers
     int out_d, out_h, out_w; // output extent actually written
     long long out_sn, out_sc, out_sd;   // element strides of sample, channel, depth in the dense fp32 output
@@ -127,6 +129,9 @@ __device__ __forceinline__ JobCoord decode_job(const TcParams& p, int job) {
     return j;
 }
 
+// Epilogue register budget: each of the 8 epilogue warps owns one TMEM lane quarter (warp_id % 4) and one half of the
+// output channels, i.e. CPH = cout_pad / 2 columns of D0 (and of D1 in split mode) per thread.
+template <int CPH, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w, const __grid_constant__ TcParams p,
@@ -142,23 +147,24 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     uint32_t* tmem_addr_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* s_bias = reinterpret_cast<float*>(tmem_addr_slot + 4);
 
+    constexpr int kCoutPad = 2 * CPH;
+    constexpr int kAccCols = SPLIT ? 2 * kCoutPad : kCoutPad;   // TMEM columns of one accumulator buffer (= p.nb)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         prefetch_tensormap(&map_a_hi);
-        if (p.split) prefetch_tensormap(&map_a_lo);
+        if (SPLIT) prefetch_tensormap(&map_a_lo);
         prefetch_tensormap(&map_w);
         for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
         fence_barrier_init();
     }
-    for (int i = threadIdx.x; i < p.cout_pad; i += kThreads) s_bias[i] = i < p.cout ? bias[i] : 0.f;
+    for (int i = threadIdx.x; i < kCoutPad; i += kThreads) s_bias[i] = i < p.cout ? bias[i] : 0.f;
     if (warp == 1) tmem_alloc<512>(tmem_addr_slot);      // one CTA per SM: take the whole TMEM (2 accumulator buffers)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_addr_slot;
-    const int acc_cols = p.nb;                            // columns per accumulator buffer (<= 256)
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -176,10 +182,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     for (int cb = 0; cb < p.ncb; ++cb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* st = ring + static_cast<size_t>(stage) * p.stage_bytes;
-                        mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes * (p.split ? 2 : 1) + p.b_tx);
+                        mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes * (SPLIT ? 2 : 1) + p.b_tx);
                         tma_load_5d(st, &map_a_hi, &full_bar[stage], cb * p.kc, cw, chh, cd, jc.n);
-                        if (p.split) tma_load_5d(st + p.a_bytes, &map_a_lo, &full_bar[stage], cb * p.kc, cw, chh, cd, jc.n);
-                        tma_load_2d(st + p.a_bytes * (p.split ? 2 : 1), &map_w, &full_bar[stage], 0,
+                        if (SPLIT) tma_load_5d(st + p.a_bytes, &map_a_lo, &full_bar[stage], cb * p.kc, cw, chh, cd, jc.n);
+                        tma_load_2d(st + p.a_bytes * (SPLIT ? 2 : 1), &map_w, &full_bar[stage], 0,
                                     (static_cast<int>(te.widx) * p.ncb + cb) * p.nb);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
@@ -188,11 +194,15 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // The tensor core accumulates in fp32 with truncation, so a long accumulation chain drifts (measured: 6e-3 px
+        // of disparity over NVSmall).  Chains are therefore kept short: one chunk = p.chunk_kb K blocks (one filter
+        // tap in split mode) accumulates in TMEM, then the epilogue warps add it into fp32 registers (round-to-nearest)
+        // while the next chunk runs in the other TMEM buffer.
         if (lane == 0) {
             const uint32_t pitch = p.kc * 2;                                   // bytes per operand row = swizzle span
             const uint32_t swz = p.kc == 64 ? 2u : (p.kc == 32 ? 4u : 6u);     // SWIZZLE_128B / 64B / 32B
-            const uint32_t idesc_full = umma_idesc_f16(kTileM, p.nb);
-            const uint32_t idesc_half = umma_idesc_f16(kTileM, p.cout_pad);
+            const uint32_t idesc_full = umma_idesc_f16(kTileM, kAccCols);
+            const uint32_t idesc_half = umma_idesc_f16(kTileM, kCoutPad);
             int stage = 0;
             uint32_t phase = 0;
             int buf = 0;
@@ -200,76 +210,98 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
                 const JobCoord jc = decode_job(p, job);
                 const int nkb = p.cls[jc.cls].ntaps * p.ncb;
-                mbar_wait(&tmem_empty[buf], buf_phase[buf] ^ 1);               // epilogue drained this buffer
-                tc_fence_after();
-                const uint32_t d0 = tmem_base + static_cast<uint32_t>(buf * acc_cols);
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                for (int kb0 = 0; kb0 < nkb; kb0 += p.chunk_kb) {
+                    const int kb1 = min(nkb, kb0 + p.chunk_kb);
+                    mbar_wait(&tmem_empty[buf], buf_phase[buf] ^ 1);           // epilogue drained this buffer
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(ring + static_cast<size_t>(stage) * p.stage_bytes);
-                    const uint32_t a_lo = a_hi + p.a_bytes;
-                    const uint32_t b = a_hi + p.a_bytes * (p.split ? 2 : 1);
-                    for (int kk = 0; kk < p.kc / 16; ++kk) {
-                        const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
-                        const uint64_t da = umma_smem_desc(a_hi + kk * 32, pitch, swz, 0);
-                        const uint64_t db = umma_smem_desc(b + kk * 32, pitch, swz, 0);
-                        umma_f16(d0, da, db, idesc_full, acc);                 // [A_hi*W_hi | A_hi*W_lo]
-                        if (p.split) {
-                            const uint64_t dl = umma_smem_desc(a_lo + kk * 32, pitch, swz, 0);
-                            umma_f16(d0 + p.cout_pad, dl, db, idesc_half, 1u); // += A_lo*W_hi into the cross-term columns
+                    const uint32_t d0 = tmem_base + static_cast<uint32_t>(buf * kAccCols);
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_u32(ring + static_cast<size_t>(stage) * p.stage_bytes);
+                        const uint32_t a_lo = a_hi + p.a_bytes;
+                        const uint32_t b = a_hi + p.a_bytes * (SPLIT ? 2 : 1);
+                        for (int kk = 0; kk < p.kc / 16; ++kk) {
+                            const uint32_t acc = (kb > kb0 || kk > 0) ? 1u : 0u;
+                            const uint64_t da = umma_smem_desc(a_hi + kk * 32, pitch, swz, 0);
+                            const uint64_t db = umma_smem_desc(b + kk * 32, pitch, swz, 0);
+                            umma_f16(d0, da, db, idesc_full, acc);             // [A_hi*W_hi | A_hi*W_lo]
+                            if (SPLIT) {
+                                const uint64_t dl = umma_smem_desc(a_lo + kk * 32, pitch, swz, 0);
+                                umma_f16(d0 + kCoutPad, dl, db, idesc_half, 1u);   // += A_lo*W_hi into the cross-term columns
+                            }
                         }
+                        umma_commit(&empty_bar[stage]);                        // slot free once these MMAs retire
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&empty_bar[stage]);                            // slot free once these MMAs retire
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    umma_commit(&tmem_full[buf]);                              // chunk complete
+                    buf_phase[buf] ^= 1;
+                    buf ^= 1;
                 }
-                umma_commit(&tmem_full[buf]);                                  // accumulator complete
-                buf_phase[buf] ^= 1;
-                buf ^= 1;
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        // ===================== epilogue (warps 2..9) =====================
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access (warp_id % 4)
+        const int half = (warp - 2) >> 2;                // which half of the output channels
         const int m = q * 32 + lane;                     // tile row = output position within the patch
         const int hl = m / p.tw, wl = m % p.tw;
+        const int col0 = half * CPH;
         int buf = 0;
         uint32_t buf_phase[2] = {0, 0};
         for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
             const JobCoord jc = decode_job(p, job);
             const ClassInfo& ci = p.cls[jc.cls];
-            mbar_wait(&tmem_full[buf], buf_phase[buf]);
-            tc_fence_after();
-            const int hi_ = jc.h0 + hl, wi_ = jc.w0 + wl;
-            const bool valid = hi_ < ci.hc && wi_ < ci.wc;
-            const int od = jc.d * p.out_s[0] + ci.ed, oh = hi_ * p.out_s[1] + ci.eh, ow = wi_ * p.out_s[2] + ci.ew;
-            const long long obase = jc.n * p.out_sn + od * p.out_sd + static_cast<long long>(oh) * p.out_w + ow;
-            const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * acc_cols);
-            for (int c0 = 0; c0 < p.cout_pad; c0 += 16) {
-                uint32_t v0[16], v1[16];
-                tmem_ld16(trow + c0, v0);
-                if (p.split) tmem_ld16(trow + p.cout_pad + c0, v1);
-                tmem_ld_wait();
-                if (valid) {
+            const int nkb = ci.ntaps * p.ncb;
+            float acc0[CPH];
+            float acc1[SPLIT ? CPH : 1];
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        const int c = c0 + k;
-                        if (c < p.cout) {
-                            float val = __uint_as_float(v0[k]);
-                            if (p.split) val = fmaf(__uint_as_float(v1[k]), 1.f / 2048.f, val);
-                            val += s_bias[c];
-                            const long long idx = obase + c * p.out_sc;
-                            if (skip) val += __ldg(skip + idx);
-                            if (p.fuse_elu) val = elu1(val);
-                            out[idx] = val;
-                        }
+            for (int k = 0; k < CPH; ++k) acc0[k] = 0.f;
+            if (SPLIT) {
+#pragma unroll
+                for (int k = 0; k < CPH; ++k) acc1[k] = 0.f;
+            }
+            for (int kb0 = 0; kb0 < nkb; kb0 += p.chunk_kb) {
+                mbar_wait(&tmem_full[buf], buf_phase[buf]);
+                tc_fence_after();
+                const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * kAccCols + col0);
+                constexpr int LW = CPH >= 16 ? 16 : 8;   // columns per tcgen05.ld
+#pragma unroll
+                for (int c0 = 0; c0 < CPH; c0 += LW) {
+                    uint32_t v0[LW], v1[LW];
+                    tmem_ld<LW>(trow + c0, v0);
+                    if (SPLIT) tmem_ld<LW>(trow + kCoutPad + c0, v1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < LW; ++k) {
+                        acc0[c0 + k] += __uint_as_float(v0[k]);
+                        if (SPLIT) acc1[c0 + k] += __uint_as_float(v1[k]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                buf_phase[buf] ^= 1;
+                buf ^= 1;
+            }
+            const int hi_ = jc.h0 + hl, wi_ = jc.w0 + wl;
+            if (hi_ < ci.hc && wi_ < ci.wc) {
+                const int od = jc.d * p.out_s[0] + ci.ed, oh = hi_ * p.out_s[1] + ci.eh, ow = wi_ * p.out_s[2] + ci.ew;
+                const long long obase = jc.n * p.out_sn + od * p.out_sd + static_cast<long long>(oh) * p.out_w + ow;
+#pragma unroll
+                for (int k = 0; k < CPH; ++k) {
+                    const int c = col0 + k;
+                    if (c < p.cout) {
+                        float val = acc0[k];
+                        if (SPLIT) val = fmaf(acc1[k], 1.f / 2048.f, val);
+                        val += s_bias[c];
+                        const long long idx = obase + c * p.out_sc;
+                        if (skip) val += __ldg(skip + idx);
+                        if (p.fuse_elu) val = elu1(val);
+                        out[idx] = val;
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-            buf_phase[buf] ^= 1;
-            buf ^= 1;
         }
     }
     tc_fence_before();
@@ -313,7 +345,9 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     if (cin % 16 != 0 || cin < 16) return RT_ERR_UNSUPPORTED;
     if (cin > 64 && cin % 64 != 0) return RT_ERR_UNSUPPORTED;
     if (cin < 64 && cin != 16 && cin != 32) return RT_ERR_UNSUPPORTED;
-    const int cout_pad = (cout + 15) / 16 * 16;
+    int cout_pad = 16;
+    while (cout_pad < cout) cout_pad *= 2;
+    if (cout_pad > 128) return RT_ERR_UNSUPPORTED;
     const bool split = d.precision == RT_PREC_FP32;
     const int nb = split ? 2 * cout_pad : cout_pad;
     if (nb > 256) return RT_ERR_UNSUPPORTED;
@@ -444,6 +478,7 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     p.b_tx = nb * p.kc * 2;
     p.b_bytes = (p.b_tx + 1023) & ~1023;
     p.stage_bytes = p.a_bytes * (split ? 2 : 1) + p.b_bytes;
+    p.chunk_kb = split ? p.ncb : (1 << 30);      // split mode: flush every filter tap; fp16 mode: one chain per tile
     p.stages = (196 * 1024) / p.stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) { cudaFree(t->w_dev); delete t; return RT_ERR_UNSUPPORTED; }
@@ -463,8 +498,8 @@ void tc_plan_destroy(rt_conv3d_plan* plan) {
 
 size_t tc_workspace_size(const rt_conv3d_plan* plan, int max_batch) {
     const TcPlan* t = static_cast<const TcPlan*>(plan->tc);
-    const size_t per = (t->in_elems * 2 + 255) & ~static_cast<size_t>(255);
-    return per * (t->p.split ? 2 : 1) * static_cast<size_t>(max_batch) + 256;
+    const size_t part = (t->in_elems * 2 * static_cast<size_t>(max_batch) + 255) & ~static_cast<size_t>(255);
+    return part * (t->p.split ? 2 : 1) + 256;
 }
 
 int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const float* skip, float* y, void* workspace,
@@ -474,11 +509,10 @@ int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const f
     TcParams p = t->p;
     p.njobs = p.jobs_per_sample * n;
     if (p.njobs == 0) return RT_OK;
-    const size_t per = (t->in_elems * 2 + 255) & ~static_cast<size_t>(255);
+    // Samples are packed back to back (the 5-D tensor map strides over them); the lo plane follows the hi plane.
+    const size_t part = (t->in_elems * 2 * static_cast<size_t>(n) + 255) & ~static_cast<size_t>(255);
     __half* hi = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
-    __half* lo = p.split ? reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(hi) + per * n) : nullptr;
-    // When n > 1 the per-sample blocks must be contiguous for the 5-D tensor map: per == in_elems*2 unless padded.
-    if (n > 1 && per != t->in_elems * 2) return RT_ERR_UNSUPPORTED;
+    __half* lo = p.split ? reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(hi) + part) : nullptr;
 
     // 1. pack
     {
@@ -507,14 +541,25 @@ int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const f
         if (!p.split) ma_lo = ma_hi;
     }
     // 3. main kernel
-    static bool attr_set = false;
-    if (!attr_set) {
-        RT_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
     int grid = num_sms();
     if (grid > p.njobs) grid = p.njobs;
-    conv3d_umma_kernel<<<grid, kThreads, t->smem_bytes, s>>>(ma_hi, ma_lo, t->map_w, p, plan->bias, skip, y);
+#define RT_LAUNCH_UMMA(CPH, SPL)                                                                                      \
+    do {                                                                                                              \
+        static bool attr_set = false;                                                                                 \
+        if (!attr_set) {                                                                                              \
+            RT_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<CPH, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            attr_set = true;                                                                                          \
+        }                                                                                                             \
+        conv3d_umma_kernel<CPH, SPL><<<grid, kThreads, t->smem_bytes, s>>>(ma_hi, ma_lo, t->map_w, p, plan->bias, skip, y); \
+    } while (0)
+    switch (p.cout_pad) {
+        case 16:  if (p.split) RT_LAUNCH_UMMA(8, true);  else RT_LAUNCH_UMMA(8, false);  break;
+        case 32:  if (p.split) RT_LAUNCH_UMMA(16, true); else RT_LAUNCH_UMMA(16, false); break;
+        case 64:  if (p.split) RT_LAUNCH_UMMA(32, true); else RT_LAUNCH_UMMA(32, false); break;
+        case 128: if (p.split) RT_LAUNCH_UMMA(64, true); else RT_LAUNCH_UMMA(64, false); break;
+        default: return RT_ERR_UNSUPPORTED;
+    }
+#undef RT_LAUNCH_UMMA
     note_launch(p.split ? "conv3d_umma_fp16x2split" : "conv3d_umma_fp16");
     RT_CHECK_LAUNCH();
     return RT_OK;
