@@ -52,6 +52,18 @@ inline int make_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, int rank
 // ---------------------------------------------------------------------------------------------------------------
 // Device: mbarrier.
 // ---------------------------------------------------------------------------------------------------------------
+// One lane of the (fully converged) warp; ptxas knows the guarded region is single-threaded and emits
+// warp-level instructions (UTCHMMA, UTMALDG, UTCBAR) straight-line instead of per-active-lane loops.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
