@@ -513,6 +513,33 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                     out = net.layers_[nxt]->d.out[0];
                     st.name += " + " + net.layers_[nxt]->d.name;
                 }
+                // A 2-D convolution is a 3-D one with V = D = 1: when the channel counts fit the tensor-core tiles the
+                // tower convs run on the same tcgen05 implicit-GEMM kernel as the 3-D stack ([K,1,H,W] == [K,H,W]).
+                const char* pe2 = getenv("REDTAIL_CONV3D_PRECISION");
+                const bool simt_only = pe2 && !strcmp(pe2, "simt");
+                if (fusion && !simt_only && d.kind == LKind::kConv && cd.cin % 16 == 0 && cd.cout <= 128) {
+                    rt_conv3d_desc c3{};
+                    c3.k = cd.cout; c3.v = 1; c3.c = cd.cin; c3.r = cd.r; c3.s = cd.s;
+                    c3.stride[0] = 1; c3.stride[1] = cd.stride[0]; c3.stride[2] = cd.stride[1];
+                    c3.pad[0] = 0; c3.pad[1] = cd.pad[0]; c3.pad[2] = cd.pad[1];
+                    c3.in_dims[0] = 1; c3.in_dims[1] = cd.cin; c3.in_dims[2] = cd.in_h; c3.in_dims[3] = cd.in_w;
+                    c3.out_dims[0] = cd.cout; c3.out_dims[1] = 1;
+                    c3.out_dims[2] = out->dims.d[1]; c3.out_dims[3] = out->dims.d[2];
+                    c3.weights_dtype = cd.weights_dtype; c3.weights = cd.weights; c3.bias = cd.bias;
+                    c3.precision = pe2 && !strcmp(pe2, "fp16") ? RT_PREC_FP16 : RT_PREC_FP32;
+                    c3.fuse_elu = cd.fuse_elu;
+                    rt_conv3d_plan* p3 = nullptr;
+                    if (rt_conv3d_create(&c3, &p3) == RT_OK) {
+                        conv3d_plans_.push_back(p3);
+                        st.workspace = rt_conv3d_workspace_size(p3, max_batch_);
+                        const int in_id = d.in[0]->id, out_id = out->id;
+                        st.out.push_back(out_id);
+                        st.run = [p3, in_id, out_id](int batch, const std::function<void*(int)>& ptr, void* ws, cudaStream_t s) {
+                            return rt_conv3d_enqueue(p3, batch, ptr(in_id), nullptr, ptr(out_id), ws, s);
+                        };
+                        break;
+                    }
+                }
                 rt_conv2d_plan* plan = nullptr;
                 const int rc = rt_conv2d_create(&cd, &plan);
                 if (rc != RT_OK) return fail(d.name + ": rt_conv2d_create failed (" + std::to_string(rc) + ")");
