@@ -42,10 +42,13 @@ constexpr int kTileM = 128;
 
 struct TapEntry { int8_t dd, dh, dw; uint8_t widx; };     // A-coordinate offsets, weight tap index
 
+// A "class" is one independent implicit GEMM over the input lattice.  Forward conv: one class, all taps.
+// Transposed conv of stride s (sub-pixel formulation): output parities that are MERGED ride along GEMM-N (columns =
+// [parity_d][parity_h][channel][parity_w]) and share the A tiles; the remaining parities are separate classes.
 struct ClassInfo {
-    int ntaps;
-    int ed, eh, ew;          // output offset within the stride-s lattice (0 for forward conv)
-    int dc, hc, wc;          // class-local output extent
+    int ntaps;               // number of A shifts of this class
+    int ed, eh, ew;          // output parity of the un-merged dims (0 for merged dims / forward conv)
+    int dc, hc, wc;          // class-local extent of the GEMM-M lattice
     int tiles_h, tiles_w;
     int job_begin;           // first job index of this class (per sample)
     TapEntry taps[kMaxTaps];
@@ -59,7 +62,9 @@ struct TcParams {
     int th, tw;
     int kc, ncb;             // channels per K block, K blocks per tap
     int cout, nb;            // real output channels, GEMM-N of the B tile (2*cout_pad in fp32 mode)
-    int cout_pad;
+    int cout_pad;            // accumulator columns (power of two, >= 16)
+    int ncols;               // columns that map to an output: cpc << (ld + lh + lw)
+    int lc, ld, lh, lw;      // log2 of: channels per parity class, merged parities along D, H, W
     int split;               // 1: hi/lo operands (RT_PREC_FP32), 0: hi only
     int stages;
     int chunk_kb;            // K blocks accumulated in TMEM before the epilogue adds them up in fp32 registers
@@ -296,16 +301,22 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             }
             const int hi_ = jc.h0 + hl, wi_ = jc.w0 + wl;
             if (hi_ < ci.hc && wi_ < ci.wc) {
-                const int od = jc.d * p.out_s[0] + ci.ed, oh = hi_ * p.out_s[1] + ci.eh, ow = wi_ * p.out_s[2] + ci.ew;
-                const long long obase = jc.n * p.out_sn + od * p.out_sd + static_cast<long long>(oh) * p.out_w + ow;
+                const int bd = jc.d * p.out_s[0] + ci.ed, bh = hi_ * p.out_s[1] + ci.eh, bw = wi_ * p.out_s[2] + ci.ew;
+                const long long nbase = jc.n * p.out_sn;
+                const int mw = (1 << p.lw) - 1, mc = (1 << p.lc) - 1, mh = (1 << p.lh) - 1;
 #pragma unroll
                 for (int k = 0; k < CPH; ++k) {
-                    const int c = col0 + k;
-                    if (c < p.cout) {
+                    const int col = col0 + k;               // column -> (parity_d, parity_h, channel, parity_w)
+                    const int pw_ = col & mw;
+                    int t = col >> p.lw;
+                    const int c = t & mc;
+                    t >>= p.lc;
+                    const int od = bd + (t >> p.lh), oh = bh + (t & mh), ow = bw + pw_;
+                    if (col < p.ncols && c < p.cout && od < p.out_d && oh < p.out_h && ow < p.out_w) {
                         float val = acc0[k];
                         if (SPLIT) val = fmaf(acc1[k], 1.f / 2048.f, val);
                         val += s_bias[c];
-                        const long long idx = obase + c * p.out_sc;
+                        const long long idx = nbase + od * p.out_sd + c * p.out_sc + static_cast<long long>(oh) * p.out_w + ow;
                         if (skip) val += __ldg(skip + idx);
                         if (p.fuse_elu) val = elu1(val);
                         out[idx] = val;
@@ -355,9 +366,22 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     if (cin % 16 != 0 || cin < 16) return RT_ERR_UNSUPPORTED;
     if (cin > 64 && cin % 64 != 0) return RT_ERR_UNSUPPORTED;
     if (cin < 64 && cin != 16 && cin != 32) return RT_ERR_UNSUPPORTED;
+    // Channels per parity class (power of two) and which stride-2 output parities are merged into GEMM-N.
+    int cpc = 1;
+    while (cpc < cout) cpc *= 2;
+    if (cpc > 128) return RT_ERR_UNSUPPORTED;
+    int lmerge[3] = {0, 0, 0};
+    if (tr) {
+        int ncol = cpc;
+        const int order[3] = {2, 1, 0};                  // merge W first (adjacent outputs), then H, then D
+        for (int oi = 0; oi < 3; ++oi) {
+            const int i = order[oi];
+            if (d.stride[i] == 2 && ncol * 2 <= 128) { lmerge[i] = 1; ncol *= 2; }
+        }
+    }
+    const int ncols = cpc << (lmerge[0] + lmerge[1] + lmerge[2]);
     int cout_pad = 16;
-    while (cout_pad < cout) cout_pad *= 2;
-    if (cout_pad > 128) return RT_ERR_UNSUPPORTED;
+    while (cout_pad < ncols) cout_pad *= 2;
     const bool split = d.precision == RT_PREC_FP32;
     const int nb = split ? 2 * cout_pad : cout_pad;
     if (nb > 256) return RT_ERR_UNSUPPORTED;
@@ -400,13 +424,22 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     t->in_elems = static_cast<size_t>(t->in_sn);
     p.out_d = out_ext[0]; p.out_h = out_ext[1]; p.out_w = out_ext[2];
 
-    // Parity classes and their tap tables.
+    p.ncols = ncols;
+    p.lc = 0;
+    while ((1 << p.lc) < cpc) ++p.lc;
+    p.ld = lmerge[0]; p.lh = lmerge[1]; p.lw = lmerge[2];
+
+    // Classes (un-merged output parities) and their A-shift tables.
     int ncls[3];
-    for (int i = 0; i < 3; ++i) ncls[i] = tr ? d.stride[i] : 1;
+    for (int i = 0; i < 3; ++i) ncls[i] = (tr && !lmerge[i]) ? d.stride[i] : 1;
     p.nclasses = ncls[0] * ncls[1] * ncls[2];
-    // Patch shape: minimise padded area over the class-local extents (use the largest class = class 0).
-    const int cls_h = tr ? (out_ext[1] + d.stride[1] - 1) / d.stride[1] : out_ext[1];
-    const int cls_w = tr ? (out_ext[2] + d.stride[2] - 1) / d.stride[2] : out_ext[2];
+    // GEMM-M lattice extent per dim: outputs / stride (rounded up) for the transposed conv.
+    auto lattice = [&](int i, int e) {
+        if (!tr) return out_ext[i];
+        const int v2 = lmerge[i] ? (out_ext[i] + d.stride[i] - 1) / d.stride[i] : (out_ext[i] - e + d.stride[i] - 1) / d.stride[i];
+        return v2 > 0 ? v2 : 0;
+    };
+    const int cls_h = lattice(1, 0), cls_w = lattice(2, 0);
     long long best = -1;
     for (int tw = 8; tw <= 128; tw *= 2) {
         const int th = kTileM / tw;
@@ -414,6 +447,14 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
         const long long area = static_cast<long long>((cls_w + tw - 1) / tw) * tw * ((cls_h + th - 1) / th) * th;
         if (best < 0 || area < best) { best = area; p.tw = tw; p.th = th; }
     }
+    // For (class parity e, merged parity em, shift off) the filter tap along dim i, or -1 when that parity does not
+    // use that shift:  forward conv: tap = off + pad;  transposed: tap = e + pad - stride * off.
+    auto tap_of = [&](int i, int e, int off) {
+        const int tp = tr ? e + d.pad[i] - d.stride[i] * off : off + d.pad[i];
+        return (tp >= 0 && tp < kdim[i]) ? tp : -1;
+    };
+    struct Tile { int cls; int off[3]; };
+    std::vector<Tile> tiles;
     int job = 0, ci = 0;
     for (int ed = 0; ed < ncls[0]; ++ed)
         for (int eh = 0; eh < ncls[1]; ++eh)
@@ -421,54 +462,63 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
                 ClassInfo& c = p.cls[ci];
                 c.ed = ed; c.eh = eh; c.ew = ew;
                 const int e[3] = {ed, eh, ew};
-                int ext[3];
-                for (int i = 0; i < 3; ++i) ext[i] = tr ? (out_ext[i] - e[i] + d.stride[i] - 1) / d.stride[i] : out_ext[i];
-                c.dc = ext[0] > 0 ? ext[0] : 0; c.hc = ext[1] > 0 ? ext[1] : 0; c.wc = ext[2] > 0 ? ext[2] : 0;
+                c.dc = lattice(0, ed); c.hc = lattice(1, eh); c.wc = lattice(2, ew);
                 c.tiles_h = (c.hc + p.th - 1) / p.th; c.tiles_w = (c.wc + p.tw - 1) / p.tw;
                 c.job_begin = job;
                 job += c.dc * c.tiles_h * c.tiles_w;
                 c.ntaps = 0;
-                for (int v = 0; v < d.v; ++v)
-                    for (int r = 0; r < d.r; ++r)
-                        for (int s = 0; s < d.s; ++s) {
-                            const int tap[3] = {v, r, s};
-                            int off[3];
-                            bool ok = true;
-                            for (int i = 0; i < 3; ++i) {
-                                if (!tr) off[i] = tap[i] - d.pad[i];
-                                else {
-                                    const int num = e[i] + d.pad[i] - tap[i];
-                                    // floor-mod so that negative numerators classify correctly
-                                    if (((num % d.stride[i]) + d.stride[i]) % d.stride[i] != 0) { ok = false; break; }
-                                    off[i] = num >= 0 ? num / d.stride[i] : -((-num) / d.stride[i]);
-                                }
-                            }
-                            if (!ok) continue;
+                // candidate shifts per dim: every offset for which at least one (merged) parity has a valid tap
+                std::vector<int> offs[3];
+                for (int i = 0; i < 3; ++i)
+                    for (int off = -4; off <= 4; ++off) {
+                        bool any = false;
+                        for (int em = 0; em <= lmerge[i]; ++em) any = any || tap_of(i, lmerge[i] ? em : e[i], off) >= 0;
+                        if (any) offs[i].push_back(off);
+                    }
+                for (int od : offs[0])
+                    for (int oh : offs[1])
+                        for (int ow : offs[2]) {
+                            if (c.ntaps >= kMaxTaps || tiles.size() >= 255) { delete t; return RT_ERR_UNSUPPORTED; }
                             TapEntry te;
-                            te.dd = static_cast<int8_t>(off[0]); te.dh = static_cast<int8_t>(off[1]); te.dw = static_cast<int8_t>(off[2]);
-                            te.widx = static_cast<uint8_t>((v * d.r + r) * d.s + s);
+                            te.dd = static_cast<int8_t>(od); te.dh = static_cast<int8_t>(oh); te.dw = static_cast<int8_t>(ow);
+                            te.widx = static_cast<uint8_t>(tiles.size());
                             c.taps[c.ntaps++] = te;
+                            tiles.push_back(Tile{ci, {od, oh, ow}});
                         }
             }
     p.jobs_per_sample = job;
 
-    // Weight packing: [tap][cb][row][kc] fp16; rows 0..cout_pad-1 = hi, rows cout_pad.. = lo (fp32 mode).
-    const int ntap = d.v * d.r * d.s;
+    // Weight packing: [tile][cb][row][kc] fp16; row = accumulator column (hi), cout_pad + column (lo, fp32 mode).
+    const int ntap = static_cast<int>(tiles.size());
     std::vector<uint16_t> pk(static_cast<size_t>(ntap) * p.ncb * nb * p.kc, 0);
-    for (int k = 0; k < d.k; ++k)
-        for (int v = 0; v < d.v; ++v)
-            for (int c = 0; c < d.c; ++c)
-                for (int r = 0; r < d.r; ++r)
-                    for (int s = 0; s < d.s; ++s) {
-                        float val = w[(((static_cast<size_t>(k) * d.v + v) * d.c + c) * d.r + r) * d.s + s];
-                        val = val > 65504.f ? 65504.f : (val < -65504.f ? -65504.f : val);
-                        const int co = tr ? c : k, ci2 = tr ? k : c;
-                        const int tap = (v * d.r + r) * d.s + s;
-                        const size_t base = ((static_cast<size_t>(tap) * p.ncb + ci2 / p.kc) * nb) * p.kc + (ci2 % p.kc);
-                        const uint16_t hb = f2h_bits(val);
-                        pk[base + static_cast<size_t>(co) * p.kc] = hb;
-                        if (split) pk[base + static_cast<size_t>(cout_pad + co) * p.kc] = f2h_bits((val - h2f_bits(hb)) * 2048.f);
-                    }
+    for (int ti = 0; ti < ntap; ++ti) {
+        const ClassInfo& c = p.cls[tiles[ti].cls];
+        const int e[3] = {c.ed, c.eh, c.ew};
+        for (int col = 0; col < ncols; ++col) {
+            const int pw_ = col & ((1 << p.lw) - 1);
+            int tt = col >> p.lw;
+            const int ch = tt & (cpc - 1);
+            tt >>= p.lc;
+            const int em[3] = {tt >> p.lh, tt & ((1 << p.lh) - 1), pw_};
+            if (ch >= cout) continue;
+            int tp[3];
+            bool ok = true;
+            for (int i = 0; i < 3; ++i) {
+                tp[i] = tap_of(i, lmerge[i] ? em[i] : e[i], tiles[ti].off[i]);
+                ok = ok && tp[i] >= 0;
+            }
+            if (!ok) continue;
+            for (int kin = 0; kin < cin; ++kin) {
+                const int kk = tr ? kin : ch, cc = tr ? ch : kin;       // KVCRS indices
+                float val = w[(((static_cast<size_t>(kk) * d.v + tp[0]) * d.c + cc) * d.r + tp[1]) * d.s + tp[2]];
+                val = val > 65504.f ? 65504.f : (val < -65504.f ? -65504.f : val);
+                const size_t base = ((static_cast<size_t>(ti) * p.ncb + kin / p.kc) * nb) * p.kc + (kin % p.kc);
+                const uint16_t hb = f2h_bits(val);
+                pk[base + static_cast<size_t>(col) * p.kc] = hb;
+                if (split) pk[base + static_cast<size_t>(cout_pad + col) * p.kc] = f2h_bits((val - h2f_bits(hb)) * 2048.f);
+            }
+        }
+    }
     if (cudaMalloc(&t->w_dev, pk.size() * 2) != cudaSuccess ||
         cudaMemcpy(t->w_dev, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaFree(t->w_dev);
