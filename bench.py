@@ -210,6 +210,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from redtail_b200 import StereoEngine, ops
+    from redtail_b200.parallel import gather_disparities
     B = args.batch
     eng = StereoEngine("nvsmall", H, W, WEIGHTS, max_batch=B)
     left_np, right_np = synthetic_pairs(B, seed=1234 + 100 * rank)
@@ -223,7 +224,7 @@ def main():
     def step_device():
         eng(d_left, d_right, out=d_disp)
         if world > 1:      # the one exchange of the path: collect every rank's disparity maps (NCCL over NVLink)
-            dist.all_gather_into_tensor(gathered, d_disp)
+            gather_disparities(d_disp, out=gathered)
 
     def barrier():
         if world > 1:
@@ -254,7 +255,7 @@ def main():
     def step_host():
         eng.execute_host(h_left, h_right, h_disp)      # H2D x2 + inference + D2H, synchronous
         if world > 1:
-            dist.all_gather_into_tensor(gathered, d_disp.copy_(h_disp, non_blocking=True))
+            gather_disparities(d_disp.copy_(h_disp, non_blocking=True), out=gathered)
     for _ in range(2):
         step_host()
     barrier()
