@@ -151,6 +151,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     uint64_t* tmem_empty = tmem_full + 8;
     uint32_t* tmem_addr_slot = reinterpret_cast<uint32_t*>(tmem_empty + 8);
     float* s_bias = reinterpret_cast<float*>(tmem_addr_slot + 4);
+    // Per accumulator column: element offset of its output relative to the thread's (parity-0) output position,
+    // its channel and its parity index pd*4 + ph*2 + pw (8 = column maps to nothing).  Tile independent.
+    struct ColInfo { long long off; int ch; int pidx; };
+    ColInfo* s_col = reinterpret_cast<ColInfo*>(s_bias + 128);
 
     constexpr int kCoutPad = 2 * CPH;
     constexpr int kAccCols = SPLIT ? 2 * kCoutPad : kCoutPad;   // TMEM columns of one accumulator buffer (= p.nb)
@@ -165,7 +169,19 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         for (int i = 0; i < kNumBuf; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
         fence_barrier_init();
     }
-    for (int i = threadIdx.x; i < kCoutPad; i += kThreads) s_bias[i] = i < p.cout ? bias[i] : 0.f;
+    for (int i = threadIdx.x; i < kCoutPad; i += kThreads) {
+        s_bias[i] = i < p.cout ? bias[i] : 0.f;
+        const int pw_ = i & ((1 << p.lw) - 1);
+        int t = i >> p.lw;
+        const int c = t & ((1 << p.lc) - 1);
+        t >>= p.lc;
+        const int ph_ = t & ((1 << p.lh) - 1), pd_ = t >> p.lh;
+        ColInfo ci;
+        ci.off = pd_ * p.out_sd + c * p.out_sc + static_cast<long long>(ph_) * p.out_w + pw_;
+        ci.ch = c;
+        ci.pidx = (i < p.ncols && c < p.cout) ? pd_ * 4 + ph_ * 2 + pw_ : 8;
+        s_col[i] = ci;
+    }
     if (warp == 1) tmem_alloc<512>(tmem_addr_slot);      // one CTA per SM: take the whole TMEM (2 accumulator buffers)
     tc_fence_before();
     __syncthreads();
@@ -302,24 +318,37 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             const int hi_ = jc.h0 + hl, wi_ = jc.w0 + wl;
             if (hi_ < ci.hc && wi_ < ci.wc) {
                 const int bd = jc.d * p.out_s[0] + ci.ed, bh = hi_ * p.out_s[1] + ci.eh, bw = wi_ * p.out_s[2] + ci.ew;
-                const long long nbase = jc.n * p.out_sn;
-                const int mw = (1 << p.lw) - 1, mc = (1 << p.lc) - 1, mh = (1 << p.lh) - 1;
+                const long long rowbase = jc.n * p.out_sn + bd * p.out_sd + static_cast<long long>(bh) * p.out_w + bw;
+                // which of the (up to 8) merged output parities of this row fall inside the output
+                uint32_t vmask = 0;
 #pragma unroll
-                for (int k = 0; k < CPH; ++k) {
-                    const int col = col0 + k;               // column -> (parity_d, parity_h, channel, parity_w)
-                    const int pw_ = col & mw;
-                    int t = col >> p.lw;
-                    const int c = t & mc;
-                    t >>= p.lc;
-                    const int od = bd + (t >> p.lh), oh = bh + (t & mh), ow = bw + pw_;
-                    if (col < p.ncols && c < p.cout && od < p.out_d && oh < p.out_h && ow < p.out_w) {
-                        float val = acc0[k];
-                        if (SPLIT) val = fmaf(acc1[k], 1.f / 2048.f, val);
-                        val += s_bias[c];
-                        const long long idx = nbase + od * p.out_sd + c * p.out_sc + static_cast<long long>(oh) * p.out_w + ow;
-                        if (skip) val += __ldg(skip + idx);
-                        if (p.fuse_elu) val = elu1(val);
-                        out[idx] = val;
+                for (int q8 = 0; q8 < 8; ++q8) {
+                    const bool ok = bd + (q8 >> 2) < p.out_d && bh + ((q8 >> 1) & 1) < p.out_h && bw + (q8 & 1) < p.out_w;
+                    vmask |= (ok ? 1u : 0u) << q8;
+                }
+                // Batches of 8 columns: all skip-tensor loads of a batch are issued before any is consumed.
+#pragma unroll
+                for (int k0 = 0; k0 < CPH; k0 += 8) {
+                    long long idx[8];
+                    float sk[8];
+                    int ch[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const ColInfo ci2 = s_col[col0 + k0 + j];
+                        const bool ok = (vmask >> ci2.pidx) & 1u;          // pidx == 8 -> never set
+                        ch[j] = ci2.ch;
+                        idx[j] = ok ? rowbase + ci2.off : -1;
+                        sk[j] = (ok && skip) ? __ldg(skip + idx[j]) : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (idx[j] >= 0) {
+                            float val = acc0[k0 + j];
+                            if (SPLIT) val = fmaf(acc1[k0 + j], 1.f / 2048.f, val);
+                            val += s_bias[ch[j]] + sk[j];
+                            if (p.fuse_elu) val = elu1(val);
+                            out[idx[j]] = val;
+                        }
                     }
                 }
             }
@@ -549,7 +578,7 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     p.stages = (196 * 1024) / p.stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) { cudaFree(t->w_dev); delete t; return RT_ERR_UNSUPPORTED; }
-    t->smem_bytes = p.stages * p.stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/ + cout_pad * 4;
+    t->smem_bytes = p.stages * p.stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/ + 512 /*bias*/ + 128 * 16 /*column table*/;
     if (t->smem_bytes < 120 * 1024) t->smem_bytes = 120 * 1024;   // > half of the SM: one CTA per SM, so the 512-column TMEM grab never contends
     plan->tc = t;
     return RT_OK;
