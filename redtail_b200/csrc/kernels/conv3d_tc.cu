@@ -40,7 +40,10 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;   // producer warp + MMA warp + epilogue warps
 constexpr int kTileM = 128;
 
-struct TapEntry { int8_t dd, dh, dw; uint8_t widx; };     // A-coordinate offsets, weight tap index
+// One pipeline stage = one A box + nr weight tiles.  nr > 1 ("row group"): the filter taps dh, dh+1, .. dh+nr-1 of a
+// stride-1 convolution read the SAME A box, nr-1 patch rows taller, at row offsets 0, tw, 2*tw (1 KB multiples, so the
+// swizzle phase is unchanged) -- the activations cross L2 -> SM once per (dd, dw) instead of once per tap.
+struct TapEntry { int8_t dd, dh, dw; uint8_t nr; uint8_t widx[3]; uint8_t pad_; };
 
 // A "class" is one independent implicit GEMM over the input lattice.  Forward conv: one class, all taps.
 // Transposed conv of stride s (sub-pixel formulation): output parities that are MERGED ride along GEMM-N (columns =
@@ -68,6 +71,7 @@ struct TcParams {
     int split;               // 1: hi/lo operands (RT_PREC_FP32), 0: hi only
     int stages;
     int chunk_kb;            // K blocks accumulated in TMEM before the epilogue adds them up in fp32 registers
+    int gr;                  // taps per row group (1 or 3)
     int a_bytes, b_bytes, b_tx, stage_bytes;   // b_bytes: 1 KB-rounded slot, b_tx: bytes the weight TMA actually delivers
     int out_d, out_h, out_w; // output extent actually written
     long long out_sn, out_sc, out_sd;   // element strides of sample, channel, depth in the dense fp32 output
@@ -207,11 +211,12 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     for (int cb = 0; cb < p.ncb; ++cb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* st = ring + static_cast<size_t>(stage) * p.stage_bytes;
-                        mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes * (SPLIT ? 2 : 1) + p.b_tx);
+                        mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes * (SPLIT ? 2 : 1) + te.nr * p.b_tx);
                         tma_load_5d(st, &map_a_hi, &full_bar[stage], cb * p.kc, cw, chh, cd, jc.n);
                         if (SPLIT) tma_load_5d(st + p.a_bytes, &map_a_lo, &full_bar[stage], cb * p.kc, cw, chh, cd, jc.n);
-                        tma_load_2d(st + p.a_bytes * (SPLIT ? 2 : 1), &map_w, &full_bar[stage], 0,
-                                    (static_cast<int>(te.widx) * p.ncb + cb) * p.nb);
+                        for (int i = 0; i < te.nr; ++i)
+                            tma_load_2d(st + p.a_bytes * (SPLIT ? 2 : 1) + i * p.b_bytes, &map_w, &full_bar[stage], 0,
+                                        (static_cast<int>(te.widx[i]) * p.ncb + cb) * p.nb);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -234,7 +239,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             const uint32_t idesc_half = umma_idesc_f16(kTileM, kCoutPad);
             const uint32_t ring_addr = smem_u32(ring);
             const uint32_t stage_bytes = p.stage_bytes, a_bytes = p.a_bytes;
-            const int kc16 = p.kc >> 4, stages = p.stages, chunk_kb = p.chunk_kb, ncb = p.ncb;
+            const int kc16 = p.kc >> 4, stages = p.stages, chunk_kb = p.chunk_kb, ncb = p.ncb, gr = p.gr;
+            const uint32_t grp_a16 = (static_cast<uint32_t>(p.tw) * pitch) >> 4;   // one patch row of A, in 16-byte units
+            const uint32_t grp_b16 = static_cast<uint32_t>(p.b_bytes) >> 4;
             int stage = 0;
             uint32_t phase = 0;
             int buf = 0;
@@ -255,10 +262,13 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         uint32_t lo_l = ((st_addr + a_bytes) >> 4) | (1u << 16);
                         uint32_t lo_b = ((st_addr + (SPLIT ? 2u : 1u) * a_bytes) >> 4) | (1u << 16);
                         if (elect_one_sync()) {
-                            for (int kk = 0; kk < kc16; ++kk) {
-                                umma_f16(d0, desc_hi | lo_a, desc_hi | lo_b, idesc_full, (kb > kb0 || kk > 0) ? 1u : 0u);
-                                if (SPLIT) umma_f16(d0 + kCoutPad, desc_hi | lo_l, desc_hi | lo_b, idesc_half, 1u);
-                                lo_a += 2; lo_l += 2; lo_b += 2;               // +32 bytes = one K=16 slice inside the swizzle atom
+                            for (int i = 0; i < gr; ++i) {                     // taps of the row group share the A box
+                                uint32_t xa = lo_a + i * grp_a16, xl = lo_l + i * grp_a16, xb = lo_b + i * grp_b16;
+                                for (int kk = 0; kk < kc16; ++kk) {
+                                    umma_f16(d0, desc_hi | xa, desc_hi | xb, idesc_full, (kb > kb0 || i > 0 || kk > 0) ? 1u : 0u);
+                                    if (SPLIT) umma_f16(d0 + kCoutPad, desc_hi | xl, desc_hi | xb, idesc_half, 1u);
+                                    xa += 2; xl += 2; xb += 2;                 // +32 bytes = one K=16 slice inside the swizzle atom
+                                }
                             }
                             umma_commit(&empty_bar[stage]);                    // slot free once these MMAs retire
                         }
@@ -484,6 +494,13 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     };
     struct Tile { int cls; int off[3]; };
     std::vector<Tile> tiles;
+    // Row groups (see TapEntry): stride-1 forward convs with 3 filter rows, when >= 3 pipeline stages still fit.
+    p.gr = 1;
+    if (!tr && d.r == 3 && d.stride[0] == 1 && d.stride[1] == 1 && d.stride[2] == 1 && !getenv("REDTAIL_TC_NOGROUP")) {
+        const int a_g = (p.th + 2) * p.tw * p.kc * 2;
+        const int b_g = (nb * p.kc * 2 + 1023) & ~1023;
+        if ((196 * 1024) / (a_g * (split ? 2 : 1) + 3 * b_g) >= 3) p.gr = 3;
+    }
     int job = 0, ci = 0;
     for (int ed = 0; ed < ncls[0]; ++ed)
         for (int eh = 0; eh < ncls[1]; ++eh)
@@ -505,14 +522,17 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
                         if (any) offs[i].push_back(off);
                     }
                 for (int od : offs[0])
-                    for (int oh : offs[1])
+                    for (size_t hi2 = 0; hi2 < offs[1].size(); hi2 += p.gr)
                         for (int ow : offs[2]) {
-                            if (c.ntaps >= kMaxTaps || tiles.size() >= 255) { delete t; return RT_ERR_UNSUPPORTED; }
-                            TapEntry te;
-                            te.dd = static_cast<int8_t>(od); te.dh = static_cast<int8_t>(oh); te.dw = static_cast<int8_t>(ow);
-                            te.widx = static_cast<uint8_t>(tiles.size());
+                            if (c.ntaps >= kMaxTaps || tiles.size() + p.gr > 255) { delete t; return RT_ERR_UNSUPPORTED; }
+                            TapEntry te{};
+                            te.dd = static_cast<int8_t>(od); te.dh = static_cast<int8_t>(offs[1][hi2]); te.dw = static_cast<int8_t>(ow);
+                            te.nr = static_cast<uint8_t>(p.gr);
+                            for (int g = 0; g < p.gr; ++g) {               // consecutive dh by construction (3 filter rows)
+                                te.widx[g] = static_cast<uint8_t>(tiles.size());
+                                tiles.push_back(Tile{ci, {od, offs[1][hi2 + g], ow}});
+                            }
                             c.taps[c.ntaps++] = te;
-                            tiles.push_back(Tile{ci, {od, oh, ow}});
                         }
             }
     p.jobs_per_sample = job;
@@ -563,10 +583,10 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
         if (rc != 0) { cudaFree(t->w_dev); delete t; return rc > 0 ? rc : RT_ERR_UNSUPPORTED; }
     }
     // Shared-memory budget.
-    p.a_bytes = kTileM * p.kc * 2;
+    p.a_bytes = (p.th + p.gr - 1) * p.tw * p.kc * 2;
     p.b_tx = nb * p.kc * 2;
     p.b_bytes = (p.b_tx + 1023) & ~1023;
-    p.stage_bytes = p.a_bytes * (split ? 2 : 1) + p.b_bytes;
+    p.stage_bytes = p.a_bytes * (split ? 2 : 1) + p.gr * p.b_bytes;
     // Split mode: a TMEM accumulation chain is at most ~8 MMA K-steps (K = 16 each) long before the epilogue adds it
     // into fp32 registers; fp16 mode: one chain per tile.
     // Chain length (MMA K-steps accumulated inside the tensor core before a round-to-nearest add in registers): 8 for
@@ -574,7 +594,7 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     // TMEM round trips are free and the reference's tightest unit-test tolerances (1e-4 on values ~200) need it.
     int chain = p.jobs_per_sample < 4 * 148 ? 2 : 8;
     if (const char* e = getenv("REDTAIL_TC_CHAIN")) chain = atoi(e) > 0 ? atoi(e) : chain;
-    p.chunk_kb = split ? (chain / (p.kc / 16) > 0 ? chain / (p.kc / 16) : 1) : (1 << 30);
+    p.chunk_kb = split ? (chain / (p.gr * (p.kc / 16)) > 0 ? chain / (p.gr * (p.kc / 16)) : 1) : (1 << 30);
     p.stages = (196 * 1024) / p.stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) { cudaFree(t->w_dev); delete t; return RT_ERR_UNSUPPORTED; }
@@ -628,7 +648,7 @@ int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const f
                                 static_cast<uint64_t>(t->cin) * 2 * t->in_w * t->in_h,
                                 static_cast<uint64_t>(t->cin) * 2 * t->in_w * t->in_h * t->in_d};
         const uint32_t box[5] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.tw * p.in_s[2]),
-                                 static_cast<uint32_t>(p.th * p.in_s[1]), 1u, 1u};
+                                 static_cast<uint32_t>((p.th + p.gr - 1) * p.in_s[1]), 1u, 1u};
         const uint32_t es[5] = {1u, static_cast<uint32_t>(p.in_s[2]), static_cast<uint32_t>(p.in_s[1]), 1u, 1u};
         const CUtensorMapSwizzle swz = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
         int rc = make_tensor_map(&ma_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, hi, dims, st, box, es, swz);
