@@ -48,6 +48,13 @@ enum { RT_OK = 0, RT_ERR_ARG = -1, RT_ERR_UNSUPPORTED = -2, RT_ERR_NO_DEVICE = -
  *   RT_PREC_SIMT   plain fp32 FMA on CUDA cores (validation path, no tensor cores).                        */
 enum { RT_PREC_FP32 = 0, RT_PREC_FP16 = 1, RT_PREC_SIMT = 2 };
 
+/* Activation layouts of the 3-D convolution path.
+ *   RT_LAYOUT_DENSE    fp32, the reference's plugin layouts ([D,C,H,W] / [K,D,H,W], batch leading).
+ *   RT_LAYOUT_SPLIT16  engine-internal: per sample two channels-last fp16 planes [D][H][W][C], `hi` then `lo`, with
+ *                      x = hi + lo / 2048 (what the tcgen05 kernel consumes; same bytes per element as fp32).  A tensor in
+ *                      this layout never needs Transform / Padding / fp32<->fp16 passes between two convolutions.   */
+enum { RT_LAYOUT_DENSE = 0, RT_LAYOUT_SPLIT16 = 1 };
+
 const char* rt_version(void);
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 uint64_t rt_launch_count(void);
@@ -61,6 +68,13 @@ int rt_cost_volume(int dtype, const void* left, const void* right, void* out,
 /* left,right [n,c,h,w] -> out [n,max_disp,h,w]:  out[d,y,x] = sum_ch left[ch,y,x]*right[ch,y,x-d] | 0 (fp32 accumulate). */
 int rt_corr_cost_volume(int dtype, const void* left, const void* right, void* out,
                         int n, int c, int h, int w, int max_disp, void* stream);
+
+/* left,right dense fp32 [n,c,h,w] -> out RT_LAYOUT_SPLIT16 [n][hi|lo][max_disp][h][w][2c] (same values as rt_cost_volume). */
+int rt_cost_volume_split16(const void* left, const void* right, void* out,
+                           int n, int c, int h, int w, int max_disp, void* stream);
+/* Layout converters: x dense fp32 [n,d,c,h,w] <-> RT_LAYOUT_SPLIT16 [n][hi|lo][d][h][w][c]  (c % 8 == 0). */
+int rt_dense_to_split16(const void* x, void* y, int n, int d, int c, int h, int w, void* stream);
+int rt_split16_to_dense(const void* x, void* y, int n, int d, int c, int h, int w, void* stream);
 
 /* ---- element-wise / data movement ------------------------------------------------------------------- */
 int rt_elu(int dtype, const void* x, void* y, int64_t count, void* stream);            /* x>0 ? x : expm1(x) */
@@ -98,9 +112,14 @@ typedef struct {
     int fuse_elu;            /* apply ELU in the epilogue                                                    */
     int out_transposed;      /* conv only: write [Do,K,Ho,Wo] instead of [K,Do,Ho,Wo] (fuses Transform{1,0,2,3}) */
     int slice_d;             /* transposed only: drop this many trailing D planes of out_dims (fuses SlicePlugin) */
+    int in_layout;           /* RT_LAYOUT_DENSE (fp32, the plugin layouts above) | RT_LAYOUT_SPLIT16                */
+    int out_layout;          /* layout of y; `skip`, when given, uses the same layout as y                          */
+    int pad_end_d;           /* conv only: this many virtual zero planes follow the input (fuses PaddingPlugin);
+                                in_dims[0] excludes them -- on the tensor-core path they are TMA out-of-bounds fill */
 } rt_conv3d_desc;
 
 int  rt_conv3d_create(const rt_conv3d_desc* desc, rt_conv3d_plan** plan);   /* repacks + uploads weights        */
+int  rt_conv3d_tc_supported(const rt_conv3d_desc* desc);   /* 1 when the tcgen05 kernels cover this shape (no allocation) */
 void rt_conv3d_destroy(rt_conv3d_plan* plan);
 size_t rt_conv3d_workspace_size(const rt_conv3d_plan* plan, int max_batch);
 /* x, y dense fp32 in the layouts of rt_conv3d_desc; `skip` (may be NULL) is added before ELU, same layout as y. */

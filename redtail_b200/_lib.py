@@ -20,7 +20,8 @@ class Conv3dDesc(C.Structure):
     _fields_ = [("transposed", C.c_int), ("k", C.c_int), ("v", C.c_int), ("c", C.c_int), ("r", C.c_int), ("s", C.c_int),
                 ("stride", C.c_int * 3), ("pad", C.c_int * 3), ("in_dims", C.c_int * 4), ("out_dims", C.c_int * 4),
                 ("weights_dtype", C.c_int), ("weights", C.c_void_p), ("bias", C.c_void_p), ("precision", C.c_int),
-                ("fuse_elu", C.c_int), ("out_transposed", C.c_int), ("slice_d", C.c_int)]
+                ("fuse_elu", C.c_int), ("out_transposed", C.c_int), ("slice_d", C.c_int),
+                ("in_layout", C.c_int), ("out_layout", C.c_int), ("pad_end_d", C.c_int)]
 
 
 class Conv2dDesc(C.Structure):
@@ -49,7 +50,11 @@ KERNEL_API = {
     "rt_concat_channels": (_I, [_I, _P, _I, _P, _I, _P, _I, _L, _P]),
     "rt_softargmax": (_I, [_I, _I, _P, _P, _I, _I, _L, _P]),
     "rt_conv3d_create": (_I, [C.POINTER(Conv3dDesc), C.POINTER(_P)]),
+    "rt_conv3d_tc_supported": (_I, [C.POINTER(Conv3dDesc)]),
     "rt_conv3d_destroy": (None, [_P]),
+    "rt_cost_volume_split16": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "rt_dense_to_split16": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "rt_split16_to_dense": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "rt_conv3d_workspace_size": (C.c_size_t, [_P, _I]),
     "rt_conv3d_enqueue": (_I, [_P, _I, _P, _P, _P, _P, _P]),
     "rt_conv2d_create": (_I, [C.POINTER(Conv2dDesc), C.POINTER(_P)]),

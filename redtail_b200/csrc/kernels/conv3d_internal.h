@@ -20,6 +20,7 @@ struct rt_conv3d_plan {
 };
 
 namespace rt {
+bool tc_shape_supported(const rt_conv3d_desc& d);
 int simt_conv3d_enqueue(const rt_conv3d_plan* p, int n, const float* x, const float* skip, float* y, cudaStream_t s);
 // Returns RT_OK and sets p->tc, or RT_ERR_UNSUPPORTED when the shape is outside what the tensor-core kernels cover
 // (the caller then fails loudly -- there is no silent fallback from a requested tensor-core precision).

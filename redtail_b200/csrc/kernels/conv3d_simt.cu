@@ -247,7 +247,8 @@ int rt_conv3d_create(const rt_conv3d_desc* d, rt_conv3d_plan** out) {
     const int* conv_out = d->transposed ? d->in_dims : d->out_dims;    // [K, Do, Ho, Wo]
     if (conv_in[1] != d->c || conv_out[0] != d->k) return RT_ERR_ARG;
     const int kk[3] = {d->v, d->r, d->s};
-    const int sp_in[3] = {conv_in[0], conv_in[2], conv_in[3]};
+    if (d->pad_end_d < 0 || (d->transposed && d->pad_end_d != 0)) return RT_ERR_ARG;
+    const int sp_in[3] = {conv_in[0] + d->pad_end_d, conv_in[2], conv_in[3]};
     for (int i = 0; i < 3; ++i) {
         const int span = sp_in[i] + 2 * d->pad[i] - kk[i];
         if (span < 0 || span / d->stride[i] + 1 != conv_out[1 + i]) return RT_ERR_ARG;
@@ -291,6 +292,10 @@ int rt_conv3d_create(const rt_conv3d_desc* d, rt_conv3d_plan** out) {
         rt_conv3d_destroy(p);
         return static_cast<int>(e);
     }
+    if (d->precision == RT_PREC_SIMT && (d->in_layout != RT_LAYOUT_DENSE || d->out_layout != RT_LAYOUT_DENSE)) {
+        rt_conv3d_destroy(p);
+        return RT_ERR_UNSUPPORTED;      // the CUDA-core validation kernels only speak the dense plugin layouts
+    }
     if (d->precision != RT_PREC_SIMT) {
         const int rc = tc_plan_init(p, w, b);
         if (rc != RT_OK) {           // no silent downgrade of a requested tensor-core precision
@@ -301,6 +306,8 @@ int rt_conv3d_create(const rt_conv3d_desc* d, rt_conv3d_plan** out) {
     *out = p;
     return RT_OK;
 }
+
+int rt_conv3d_tc_supported(const rt_conv3d_desc* d) { return d && tc_shape_supported(*d) ? 1 : 0; }
 
 void rt_conv3d_destroy(rt_conv3d_plan* p) {
     if (!p) return;

@@ -57,6 +57,10 @@ struct ClassInfo {
     TapEntry taps[kMaxTaps];
 };
 
+// Per accumulator column: element offset of its output relative to the thread's (parity-0) output position, its
+// channel and its parity index pd*4 + ph*2 + pw (8 = column maps to nothing).  Built on the host, tile independent.
+struct ColInfo { long long off; int ch; int pidx; };
+
 struct TcParams {
     int nclasses;
     int jobs_per_sample, njobs;
@@ -76,6 +80,9 @@ struct TcParams {
     int out_d, out_h, out_w; // output extent actually written
     long long out_sn, out_sc, out_sd;   // element strides of sample, channel, depth in the dense fp32 output
     int fuse_elu;
+    int out_split;           // 1: y (and skip) are RT_LAYOUT_SPLIT16, 0: dense fp32
+    int out_c;               // channels of the output tensor (split16 addressing)
+    long long out_lo;        // split16: offset of the lo plane, in halves
     ClassInfo cls[kMaxClasses];
 };
 
@@ -85,7 +92,7 @@ struct TcParams {
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pack_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int d_ext, int c_ext,
-                  int h_ext, int w_ext, long long s_n, long long s_d, long long s_c) {
+                  int h_ext, int w_ext, long long s_n, long long s_d, long long s_c, long long o_sn) {
     extern __shared__ float tile[];                    // [c_ext][65]
     const int w0 = blockIdx.x * 64;
     const int h = blockIdx.y;
@@ -96,7 +103,7 @@ pack_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* 
         tile[c * 65 + w] = (w0 + w < w_ext) ? __ldg(src + c * s_c + w0 + w) : 0.f;
     }
     __syncthreads();
-    const long long pix0 = ((static_cast<long long>(n) * d_ext + d) * h_ext + h) * w_ext + w0;
+    const long long pix0 = (static_cast<long long>(d) * h_ext + h) * w_ext + w0;      // within the sample
     const int groups = c_ext >> 3;                     // 8 channels (16 bytes of fp16) per thread-item
     for (int i = threadIdx.x; i < 64 * groups; i += 256) {
         const int w = i / groups, g = i % groups;
@@ -111,7 +118,7 @@ pack_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* 
             hv[k] = hh;
             lv[k] = __float2half_rn((v - __half2float(hh)) * 2048.f);
         }
-        const long long o = (pix0 + w) * c_ext + g * 8;
+        const long long o = n * o_sn + (pix0 + w) * c_ext + g * 8;
         *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(hv);
         if (lo) *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(lv);
     }
@@ -144,7 +151,8 @@ template <int CPH, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w, const __grid_constant__ TcParams p,
-                   const float* __restrict__ bias, const float* __restrict__ skip, float* __restrict__ out) {
+                   const float* __restrict__ bias, const ColInfo* __restrict__ cols, const float* __restrict__ skip,
+                   float* __restrict__ out) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // Carve: [stages x stage_bytes] operand ring (1024-aligned) | barriers | tmem address | bias
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -155,9 +163,6 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     uint64_t* tmem_empty = tmem_full + 8;
     uint32_t* tmem_addr_slot = reinterpret_cast<uint32_t*>(tmem_empty + 8);
     float* s_bias = reinterpret_cast<float*>(tmem_addr_slot + 4);
-    // Per accumulator column: element offset of its output relative to the thread's (parity-0) output position,
-    // its channel and its parity index pd*4 + ph*2 + pw (8 = column maps to nothing).  Tile independent.
-    struct ColInfo { long long off; int ch; int pidx; };
     ColInfo* s_col = reinterpret_cast<ColInfo*>(s_bias + 128);
 
     constexpr int kCoutPad = 2 * CPH;
@@ -175,16 +180,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     }
     for (int i = threadIdx.x; i < kCoutPad; i += kThreads) {
         s_bias[i] = i < p.cout ? bias[i] : 0.f;
-        const int pw_ = i & ((1 << p.lw) - 1);
-        int t = i >> p.lw;
-        const int c = t & ((1 << p.lc) - 1);
-        t >>= p.lc;
-        const int ph_ = t & ((1 << p.lh) - 1), pd_ = t >> p.lh;
-        ColInfo ci;
-        ci.off = pd_ * p.out_sd + c * p.out_sc + static_cast<long long>(ph_) * p.out_w + pw_;
-        ci.ch = c;
-        ci.pidx = (i < p.ncols && c < p.cout) ? pd_ * 4 + ph_ * 2 + pw_ : 8;
-        s_col[i] = ci;
+        s_col[i] = cols[i];
     }
     if (warp == 1) tmem_alloc<512>(tmem_addr_slot);      // one CTA per SM: take the whole TMEM (2 accumulator buffers)
     tc_fence_before();
@@ -328,7 +324,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             const int hi_ = jc.h0 + hl, wi_ = jc.w0 + wl;
             if (hi_ < ci.hc && wi_ < ci.wc) {
                 const int bd = jc.d * p.out_s[0] + ci.ed, bh = hi_ * p.out_s[1] + ci.eh, bw = wi_ * p.out_s[2] + ci.ew;
-                const long long rowbase = jc.n * p.out_sn + bd * p.out_sd + static_cast<long long>(bh) * p.out_w + bw;
+                const long long rowbase = p.out_split
+                    ? jc.n * p.out_sn + ((static_cast<long long>(bd) * p.out_h + bh) * p.out_w + bw) * p.out_c
+                    : jc.n * p.out_sn + bd * p.out_sd + static_cast<long long>(bh) * p.out_w + bw;
                 // which of the (up to 8) merged output parities of this row fall inside the output
                 uint32_t vmask = 0;
 #pragma unroll
@@ -336,6 +334,46 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     const bool ok = bd + (q8 >> 2) < p.out_d && bh + ((q8 >> 1) & 1) < p.out_h && bw + (q8 & 1) < p.out_w;
                     vmask |= (ok ? 1u : 0u) << q8;
                 }
+                if (p.out_split) {
+                    // RT_LAYOUT_SPLIT16 output: a batch of 8 columns = 8 consecutive channels of one output position
+                    // (guaranteed by the column order chosen on the host) -> one 16-byte store per fp16 plane.
+                    __half* oh16 = reinterpret_cast<__half*>(out);
+                    const __half* sk16 = reinterpret_cast<const __half*>(skip);
+#pragma unroll
+                    for (int k0 = 0; k0 < CPH; k0 += 8) {
+                        const ColInfo c0 = s_col[col0 + k0];
+                        if ((vmask >> c0.pidx) & 1u) {
+                            const long long idx = rowbase + c0.off;
+                            float v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                v[j] = acc0[k0 + j];
+                                if (SPLIT) v[j] = fmaf(acc1[k0 + j], 1.f / 2048.f, v[j]);
+                                v[j] += s_bias[c0.ch + j];
+                            }
+                            if (skip) {
+                                const uint4 sh = __ldg(reinterpret_cast<const uint4*>(sk16 + idx));
+                                const uint4 sl = __ldg(reinterpret_cast<const uint4*>(sk16 + p.out_lo + idx));
+                                const __half* hh = reinterpret_cast<const __half*>(&sh);
+                                const __half* ll = reinterpret_cast<const __half*>(&sl);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] += fmaf(__half2float(ll[j]), 1.f / 2048.f, __half2float(hh[j]));
+                            }
+                            __align__(16) __half hv[8];
+                            __align__(16) __half lv[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float x = p.fuse_elu ? elu1(v[j]) : v[j];
+                                x = fminf(fmaxf(x, -65504.f), 65504.f);
+                                const __half hx = __float2half_rn(x);
+                                hv[j] = hx;
+                                lv[j] = __float2half_rn((x - __half2float(hx)) * 2048.f);
+                            }
+                            *reinterpret_cast<uint4*>(oh16 + idx) = *reinterpret_cast<const uint4*>(hv);
+                            *reinterpret_cast<uint4*>(oh16 + p.out_lo + idx) = *reinterpret_cast<const uint4*>(lv);
+                        }
+                    }
+                } else
                 // Batches of 8 columns: all skip-tensor loads of a batch are issued before any is consumed.
 #pragma unroll
                 for (int k0 = 0; k0 < CPH; k0 += 8) {
@@ -381,6 +419,8 @@ struct TcPlan {
     long long in_sn = 0, in_sd = 0, in_sc = 0;   // dense fp32 input strides (sample, depth, channel)
     size_t in_elems = 0;              // per sample, = D*H*W*C
     int smem_bytes = 0;
+    bool in_split = false;            // x arrives as RT_LAYOUT_SPLIT16 (no pack pass)
+    ColInfo* d_cols = nullptr;        // device copy of the column table
 };
 
 uint16_t f2h_bits(float f) {
@@ -397,14 +437,27 @@ float h2f_bits(uint16_t b) {
 
 }  // namespace
 
+// Coverage of the tensor-core tiles (shape only; no device work).
+bool tc_shape_supported(const rt_conv3d_desc& d) {
+    const int cin = d.transposed ? d.k : d.c, cout = d.transposed ? d.c : d.k;
+    if (cin % 16 != 0 || cin < 16) return false;
+    if (cin > 64 && cin % 64 != 0) return false;
+    if (cin < 64 && cin != 16 && cin != 32) return false;
+    if (cout > 128 || cout < 1) return false;
+    if (d.v > 3 || d.r > 3 || d.s > 3) return false;
+    for (int i = 0; i < 3; ++i)
+        if (d.stride[i] > 2 || d.stride[i] < 1) return false;
+    if (d.out_layout == RT_LAYOUT_SPLIT16 && cout % 8 != 0) return false;   // 16-byte channel vectors
+    if (d.precision == RT_PREC_SIMT) return false;
+    return true;
+}
+
 int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::vector<float>& /*bias*/) {
     const rt_conv3d_desc& d = plan->desc;
     const bool tr = d.transposed != 0;
     const int cin = plan->cin, cout = plan->cout;
-    // Coverage of the tensor-core tiles.
-    if (cin % 16 != 0 || cin < 16) return RT_ERR_UNSUPPORTED;
-    if (cin > 64 && cin % 64 != 0) return RT_ERR_UNSUPPORTED;
-    if (cin < 64 && cin != 16 && cin != 32) return RT_ERR_UNSUPPORTED;
+    if (!tc_shape_supported(d)) return RT_ERR_UNSUPPORTED;
+    const bool out_split = d.out_layout == RT_LAYOUT_SPLIT16;
     // Channels per parity class (power of two) and which stride-2 output parities are merged into GEMM-N.
     int cpc = 1;
     while (cpc < cout) cpc *= 2;
@@ -467,6 +520,30 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     p.lc = 0;
     while ((1 << p.lc) < cpc) ++p.lc;
     p.ld = lmerge[0]; p.lh = lmerge[1]; p.lw = lmerge[2];
+    // Column order: dense output  -> [pd][ph][channel][pw]  (adjacent W parities leave a thread back to back);
+    //               split16 output-> [pd][ph][pw][channel]  (8 consecutive columns = one 16-byte channel vector).
+    struct ColDesc { int pd, ph, pw, c; bool valid; };
+    std::vector<ColDesc> cold(cout_pad, ColDesc{0, 0, 0, 0, false});
+    for (int col = 0; col < ncols; ++col) {
+        ColDesc cd{};
+        if (!out_split) {
+            cd.pw = col & ((1 << p.lw) - 1);
+            int tt = col >> p.lw;
+            cd.c = tt & (cpc - 1);
+            tt >>= p.lc;
+            cd.ph = tt & ((1 << p.lh) - 1);
+            cd.pd = tt >> p.lh;
+        } else {
+            cd.c = col & (cpc - 1);
+            int tt = col >> p.lc;
+            cd.pw = tt & ((1 << p.lw) - 1);
+            tt >>= p.lw;
+            cd.ph = tt & ((1 << p.lh) - 1);
+            cd.pd = tt >> p.lh;
+        }
+        cd.valid = cd.c < cout;
+        cold[col] = cd;
+    }
 
     // Classes (un-merged output parities) and their A-shift tables.
     int ncls[3];
@@ -544,12 +621,9 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
         const ClassInfo& c = p.cls[tiles[ti].cls];
         const int e[3] = {c.ed, c.eh, c.ew};
         for (int col = 0; col < ncols; ++col) {
-            const int pw_ = col & ((1 << p.lw) - 1);
-            int tt = col >> p.lw;
-            const int ch = tt & (cpc - 1);
-            tt >>= p.lc;
-            const int em[3] = {tt >> p.lh, tt & ((1 << p.lh) - 1), pw_};
-            if (ch >= cout) continue;
+            const int ch = cold[col].c;
+            const int em[3] = {cold[col].pd, cold[col].ph, cold[col].pw};
+            if (!cold[col].valid) continue;
             int tp[3];
             bool ok = true;
             for (int i = 0; i < 3; ++i) {
@@ -568,6 +642,33 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
             }
         }
     }
+    // Output addressing + device column table.
+    p.out_split = out_split ? 1 : 0;
+    p.out_c = cout;
+    if (out_split) {
+        const long long plane_elems = static_cast<long long>(p.out_d) * p.out_h * p.out_w * cout;
+        p.out_sn = 2 * plane_elems;          // halves per sample: hi plane + lo plane
+        p.out_lo = plane_elems;
+    }
+    {
+        std::vector<ColInfo> tab(128, ColInfo{0, 0, 8});
+        for (int col = 0; col < cout_pad; ++col) {
+            const ColDesc& cd = cold[col];
+            ColInfo ci2;
+            ci2.ch = cd.c;
+            ci2.pidx = cd.valid ? cd.pd * 4 + cd.ph * 2 + cd.pw : 8;
+            ci2.off = out_split ? ((static_cast<long long>(cd.pd) * p.out_h + cd.ph) * p.out_w + cd.pw) * cout + cd.c
+                                : cd.pd * p.out_sd + cd.c * p.out_sc + static_cast<long long>(cd.ph) * p.out_w + cd.pw;
+            tab[col] = ci2;
+        }
+        if (cudaMalloc(&t->d_cols, tab.size() * sizeof(ColInfo)) != cudaSuccess ||
+            cudaMemcpy(t->d_cols, tab.data(), tab.size() * sizeof(ColInfo), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(t->d_cols);
+            delete t;
+            return static_cast<int>(cudaErrorMemoryAllocation);
+        }
+    }
+    t->in_split = d.in_layout == RT_LAYOUT_SPLIT16;
     if (cudaMalloc(&t->w_dev, pk.size() * 2) != cudaSuccess ||
         cudaMemcpy(t->w_dev, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaFree(t->w_dev);
@@ -608,37 +709,40 @@ void tc_plan_destroy(rt_conv3d_plan* plan) {
     TcPlan* t = static_cast<TcPlan*>(plan->tc);
     if (!t) return;
     cudaFree(t->w_dev);
+    cudaFree(t->d_cols);
     delete t;
     plan->tc = nullptr;
 }
 
 size_t tc_workspace_size(const rt_conv3d_plan* plan, int max_batch) {
     const TcPlan* t = static_cast<const TcPlan*>(plan->tc);
-    const size_t part = (t->in_elems * 2 * static_cast<size_t>(max_batch) + 255) & ~static_cast<size_t>(255);
-    return part * (t->p.split ? 2 : 1) + 256;
+    if (t->in_split) return 0;
+    return t->in_elems * 4 * static_cast<size_t>(max_batch) + 512;     // per sample: hi plane + lo plane (fp16)
 }
 
 int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const float* skip, float* y, void* workspace,
                       cudaStream_t s) {
     const TcPlan* t = static_cast<const TcPlan*>(plan->tc);
-    if (!workspace) return RT_ERR_ARG;
+    if (!workspace && !t->in_split) return RT_ERR_ARG;
     TcParams p = t->p;
     p.njobs = p.jobs_per_sample * n;
     if (p.njobs == 0) return RT_OK;
-    // Samples are packed back to back (the 5-D tensor map strides over them); the lo plane follows the hi plane.
-    const size_t part = (t->in_elems * 2 * static_cast<size_t>(n) + 255) & ~static_cast<size_t>(255);
-    __half* hi = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
-    __half* lo = p.split ? reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(hi) + part) : nullptr;
-
-    // 1. pack
-    {
+    // Activations as two channels-last fp16 planes per sample: [n][hi | lo][D][H][W][C].
+    const __half* hi;
+    if (t->in_split) {
+        hi = reinterpret_cast<const __half*>(x);
+    } else {
+        __half* whi = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
         if (static_cast<long long>(n) * t->in_d > 65535 || t->in_h > 65535) return RT_ERR_UNSUPPORTED;
         dim3 grid((t->in_w + 63) / 64, t->in_h, n * t->in_d);
         const size_t sm = static_cast<size_t>(t->cin) * 65 * sizeof(float);
-        pack_split_kernel<<<grid, 256, sm, s>>>(x, hi, lo, t->in_d, t->cin, t->in_h, t->in_w, t->in_sn, t->in_sd, t->in_sc);
+        pack_split_kernel<<<grid, 256, sm, s>>>(x, whi, whi + t->in_elems, t->in_d, t->cin, t->in_h, t->in_w, t->in_sn,
+                                                t->in_sd, t->in_sc, static_cast<long long>(2 * t->in_elems));
         note_launch("conv3d_pack_split");
         RT_CHECK_LAUNCH();
+        hi = whi;
     }
+    const __half* lo = hi + t->in_elems;
     // 2. tensor maps over the packed activations: dims (C, W, H, D, N)
     CUtensorMap ma_hi, ma_lo;
     {
@@ -646,7 +750,7 @@ int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const f
                                   static_cast<uint64_t>(t->in_d), static_cast<uint64_t>(n)};
         const uint64_t st[4] = {static_cast<uint64_t>(t->cin) * 2, static_cast<uint64_t>(t->cin) * 2 * t->in_w,
                                 static_cast<uint64_t>(t->cin) * 2 * t->in_w * t->in_h,
-                                static_cast<uint64_t>(t->cin) * 2 * t->in_w * t->in_h * t->in_d};
+                                static_cast<uint64_t>(t->in_elems) * 4};          // sample stride: hi + lo planes
         const uint32_t box[5] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.tw * p.in_s[2]),
                                  static_cast<uint32_t>((p.th + p.gr - 1) * p.in_s[1]), 1u, 1u};
         const uint32_t es[5] = {1u, static_cast<uint32_t>(p.in_s[2]), static_cast<uint32_t>(p.in_s[1]), 1u, 1u};
@@ -666,7 +770,7 @@ int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const f
             RT_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<CPH, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
             attr_set = true;                                                                                          \
         }                                                                                                             \
-        conv3d_umma_kernel<CPH, SPL><<<grid, kThreads, t->smem_bytes, s>>>(ma_hi, ma_lo, t->map_w, p, plan->bias, skip, y); \
+        conv3d_umma_kernel<CPH, SPL><<<grid, kThreads, t->smem_bytes, s>>>(ma_hi, ma_lo, t->map_w, p, plan->bias, t->d_cols, skip, y); \
     } while (0)
     switch (p.cout_pad) {
         case 16:  if (p.split) RT_LAUNCH_UMMA(8, true);  else RT_LAUNCH_UMMA(8, false);  break;

@@ -12,6 +12,7 @@ from ._lib import kernels_lib, Conv3dDesc, Conv2dDesc
 
 RT_F32, RT_F16 = 0, 1
 PREC_FP32, PREC_FP16, PREC_SIMT = 0, 1, 2
+LAYOUT_DENSE, LAYOUT_SPLIT16 = 0, 1
 
 
 class RedtailError(RuntimeError):
@@ -51,6 +52,33 @@ def cost_volume(left, right, max_disp):
     n, c, h, w = left.shape
     out = torch.empty((n, max_disp, 2 * c, h, w), dtype=left.dtype, device=left.device)
     _check(kernels_lib().rt_cost_volume(_dt(left), _p(left), _p(right), _p(out), n, c, h, w, max_disp, _stream()), "rt_cost_volume")
+    return out
+
+
+def cost_volume_split16(left, right, max_disp):
+    """[N,C,H,W] fp32 x2 -> RT_LAYOUT_SPLIT16 cost volume: half tensor [N,2(hi|lo),D,H,W,2C]."""
+    _dev(left, right)
+    n, c, h, w = left.shape
+    out = torch.empty((n, 2, max_disp, h, w, 2 * c), dtype=torch.float16, device=left.device)
+    _check(kernels_lib().rt_cost_volume_split16(_p(left), _p(right), _p(out), n, c, h, w, max_disp, _stream()), "rt_cost_volume_split16")
+    return out
+
+
+def dense_to_split16(x):
+    """dense fp32 [N,D,C,H,W] -> half [N,2(hi|lo),D,H,W,C] with x = hi + lo/2048."""
+    _dev(x)
+    n, d, c, h, w = x.shape
+    out = torch.empty((n, 2, d, h, w, c), dtype=torch.float16, device=x.device)
+    _check(kernels_lib().rt_dense_to_split16(_p(x), _p(out), n, d, c, h, w, _stream()), "rt_dense_to_split16")
+    return out
+
+
+def split16_to_dense(x):
+    """half [N,2,D,H,W,C] -> dense fp32 [N,D,C,H,W]."""
+    _dev(x)
+    n, _, d, h, w, c = x.shape
+    out = torch.empty((n, d, c, h, w), dtype=torch.float32, device=x.device)
+    _check(kernels_lib().rt_split16_to_dense(_p(x), _p(out), n, d, c, h, w, _stream()), "rt_split16_to_dense")
     return out
 
 
@@ -158,7 +186,8 @@ class Conv3d:
     """
 
     def __init__(self, weights, bias, stride, pad_start, in_dims, out_dims=None, transposed=False,
-                 precision=PREC_FP32, fuse_elu=False, out_transposed=False, slice_d=0):
+                 precision=PREC_FP32, fuse_elu=False, out_transposed=False, slice_d=0,
+                 in_layout=LAYOUT_DENSE, out_layout=LAYOUT_DENSE, pad_end_d=0):
         w = np.ascontiguousarray(weights)
         assert w.ndim == 5 and w.dtype in (np.float32, np.float16)
         b = None if bias is None else np.ascontiguousarray(bias).astype(w.dtype)
@@ -170,7 +199,7 @@ class Conv3d:
         d.pad[:] = list(pad_start)
         d.in_dims[:] = list(in_dims)
         if not transposed:
-            sp = (in_dims[0], in_dims[2], in_dims[3])
+            sp = (in_dims[0] + pad_end_d, in_dims[2], in_dims[3])
             kk = (v, r, s)
             o = [(sp[i] + 2 * pad_start[i] - kk[i]) // stride[i] + 1 for i in range(3)]
             out_dims = (k, o[0], o[1], o[2])
@@ -182,6 +211,7 @@ class Conv3d:
         d.fuse_elu = int(fuse_elu)
         d.out_transposed = int(out_transposed)
         d.slice_d = int(slice_d)
+        d.in_layout, d.out_layout, d.pad_end_d = int(in_layout), int(out_layout), int(pad_end_d)
         self.desc = d
         self.transposed = transposed
         self.out_dims = tuple(out_dims)
@@ -192,18 +222,29 @@ class Conv3d:
         self._ws = None
 
     def __call__(self, x, skip=None):
+        """Dense layouts: fp32 tensors as documented above.  RT_LAYOUT_SPLIT16: half tensors [N,2,D,H,W,C]."""
         _dev(x, skip)
-        assert x.dtype == torch.float32
         n = x.shape[0]
-        assert tuple(x.shape[1:]) == tuple(self.desc.in_dims), (x.shape, tuple(self.desc.in_dims))
-        od = self.out_dims
-        if self.transposed:
-            shape = (n, od[0] - self.desc.slice_d, od[1], od[2], od[3])
-        elif self.desc.out_transposed:
-            shape = (n, od[1], od[0], od[2], od[3])
+        if self.desc.in_layout == LAYOUT_DENSE:
+            assert x.dtype == torch.float32
+            assert tuple(x.shape[1:]) == tuple(self.desc.in_dims), (x.shape, tuple(self.desc.in_dims))
         else:
-            shape = (n,) + od
-        y = torch.empty(shape, dtype=torch.float32, device=x.device)
+            assert x.dtype == torch.float16 and x.shape[1] == 2
+        od = self.out_dims
+        if self.desc.out_layout == LAYOUT_SPLIT16:
+            if self.transposed:
+                shape = (n, 2, od[0] - self.desc.slice_d, od[2], od[3], od[1])
+            else:
+                shape = (n, 2, od[1], od[2], od[3], od[0])
+            y = torch.empty(shape, dtype=torch.float16, device=x.device)
+        else:
+            if self.transposed:
+                shape = (n, od[0] - self.desc.slice_d, od[1], od[2], od[3])
+            elif self.desc.out_transposed:
+                shape = (n, od[1], od[0], od[2], od[3])
+            else:
+                shape = (n,) + od
+            y = torch.empty(shape, dtype=torch.float32, device=x.device)
         lib = kernels_lib()
         need = lib.rt_conv3d_workspace_size(self._plan, n)
         if need and (self._ws is None or self._ws.numel() < need):

@@ -326,3 +326,47 @@ def test_conv3d_transpose_nvsmall_class(R, prec, tol, cin, cout):
     ref = O.slice_d(O.conv3d_transpose(y.double(), w.double(), b.double(), (2, 2, 2), (0, 1, 1), od), 0, 8).float()
     op = _tconv(R, prec, y.cuda(), w.numpy(), b.numpy(), (2, 2, 2), (0, 1, 1), od, slice_d=1)
     check(op(y.cuda()), ref, tol)
+
+
+# ---- engine-internal RT_LAYOUT_SPLIT16 (channels-last fp16 hi/lo): same values as the dense plugin layouts ----
+def test_split16_roundtrip_and_cost_volume(R):
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 5, 16, 9, 37, generator=g) * 30
+    s16 = R.dense_to_split16(x.cuda())
+    back = R.split16_to_dense(s16)
+    assert (back.cpu() - x).abs().max() <= 30 * 4 * 2 ** -22          # 22 significant bits
+    l, r = torch.randn(2, 8, 11, 70, generator=g), torch.randn(2, 8, 11, 70, generator=g)
+    cv = R.split16_to_dense(R.cost_volume_split16(l.cuda(), r.cuda(), 13))
+    check(cv, O.cost_volume(l, r, 13), 4 * 2 ** -20)
+
+
+@pytest.mark.parametrize("cin,cout,stride", [(64, 32, 1), (32, 64, 2), (128, 128, 1)])
+def test_conv3d_split16_chain(R, cin, cout, stride):
+    """conv in split16 -> split16 (incl. the virtual Padding plane for the stride-2 layers) == dense plugin chain."""
+    g = torch.Generator().manual_seed(cin + 3 * cout)
+    d, h, w_ = (6, 19, 37) if stride == 1 else (8, 19, 37)
+    x = torch.randn(1, d, cin, h, w_, generator=g)
+    w = torch.randn(cout, 3, cin, 3, 3, generator=g) * (1.0 / np.sqrt(27 * cin))
+    b = torch.randn(cout, generator=g)
+    pad = (1, 1, 1) if stride == 1 else (0, 1, 1)
+    xin = O.pad_d(x, 1) if stride == 2 else x
+    ref = O.elu(O.transform(O.conv3d(xin.double(), w.double(), b.double(), (stride,) * 3, pad))).float()
+    op = R.Conv3d(w.numpy(), b.numpy(), (stride,) * 3, pad, tuple(x.shape[1:]), precision=R.PREC_FP32, fuse_elu=True,
+                  in_layout=R.LAYOUT_SPLIT16, out_layout=R.LAYOUT_SPLIT16, pad_end_d=1 if stride == 2 else 0)
+    y = R.split16_to_dense(op(R.dense_to_split16(x.cuda())))
+    check(y, ref, 2e-4)
+
+
+def test_conv3d_transpose_split16_skip(R):
+    g = torch.Generator().manual_seed(77)
+    y = torch.randn(1, 64, 4, 9, 17, generator=g)
+    w = torch.randn(64, 3, 32, 3, 3, generator=g) * 0.05
+    b = torch.randn(32, generator=g)
+    od = (9, 32, 17, 33)
+    skip = torch.randn(1, 8, 32, 17, 33, generator=g)
+    ref = O.elu(O.slice_d(O.conv3d_transpose(y.double(), w.double(), b.double(), (2, 2, 2), (0, 1, 1), od), 0, 8) + skip.double()).float()
+    op = R.Conv3d(w.numpy(), b.numpy(), (2, 2, 2), (0, 1, 1), (64, 4, 9, 17), out_dims=od, transposed=True, precision=R.PREC_FP32,
+                  slice_d=1, fuse_elu=True, in_layout=R.LAYOUT_SPLIT16, out_layout=R.LAYOUT_SPLIT16)
+    yin = R.dense_to_split16(y.permute(0, 2, 1, 3, 4).contiguous().cuda())     # [N,D,K,H,W] -> split16 [D][H][W][K]
+    out = R.split16_to_dense(op(yin, R.dense_to_split16(skip.cuda())))
+    check(out, ref, 3e-4)
