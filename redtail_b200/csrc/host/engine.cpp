@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -337,10 +338,24 @@ struct TensorSlot {
     bool used = false;
 };
 
+// A fused 3-D (transposed) convolution whose plan is created after the layout pass.
+struct ConvStep {
+    rt_conv3d_desc desc{};
+    rt_conv3d_plan* plan = nullptr;
+    int in_id = -1, out_id = -1, skip_id = -1;
+    std::string name;
+};
+
+struct PadInfo { int in_id; int planes; int layer; };
+
 struct Step {
     std::string name;
     std::vector<int> in, out;  // tensor ids (for liveness)
     size_t workspace = 0;
+    ConvStep* conv = nullptr;                                   // set for fused 3-D convolution steps
+    int costvol_c = 0, costvol_h = 0, costvol_w = 0, costvol_d = 0;   // set for concat cost-volume steps
+    bool is_transform = false;                                  // Transform{1,0,2,3} plugin step
+    bool dropped = false;
     // ptr(id) resolves a tensor id to its device pointer for this execution.
     std::function<int(int batch, const std::function<void*(int)>& ptr, void* workspace, cudaStream_t)> run;
 };
@@ -416,9 +431,11 @@ public:
     std::vector<IPlugin*> configured_plugins_;
     std::vector<rt_conv2d_plan*> conv2d_plans_;
     std::vector<rt_conv3d_plan*> conv3d_plans_;
+    std::vector<std::unique_ptr<ConvStep>> conv_steps_;
 
 private:
     bool fail(const std::string& s) { logMsg(log_, ILogger::Severity::kERROR, s); return false; }
+    bool assignLayoutsAndCreatePlans(bool fusion);
     bool planMemory();
 };
 
@@ -486,6 +503,7 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
     };
 
     std::vector<bool> done(nl, false);
+    std::map<int, PadInfo> absorbed_pad;      // conv layer index -> the PaddingPlugin folded into it
     for (int li = 0; li < nl; ++li) {
         if (done[li]) continue;
         LayerData& d = net.layers_[li]->d;
@@ -650,24 +668,49 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                         cd.fuse_elu = 1;
                         done[nxt] = true; out = net.layers_[nxt]->d.out[0]; st.name += " + " + net.layers_[nxt]->d.name;
                     }
-                    rt_conv3d_plan* plan = nullptr;
-                    int rc = rt_conv3d_create(&cd, &plan);
-                    if (rc == RT_ERR_UNSUPPORTED && cd.precision != RT_PREC_SIMT) {
-                        logMsg(log_, ILogger::Severity::kWARNING, d.name + ": shape not covered by the tcgen05 kernels, using the fp32 SIMT kernels.");
-                        cd.precision = RT_PREC_SIMT;
-                        rc = rt_conv3d_create(&cd, &plan);
+                    // A PaddingPlugin in front of this conv was absorbed: read the un-padded tensor, the zero planes are
+                    // virtual (TMA out-of-bounds fill on the tensor-core path).
+                    int in_id = d.in[0]->id;
+                    auto pit = absorbed_pad.find(li);
+                    if (pit != absorbed_pad.end()) {
+                        in_id = pit->second.in_id;
+                        cd.pad_end_d = pit->second.planes;
+                        cd.in_dims[0] -= cd.pad_end_d;
+                        st.in.clear();
+                        st.in.push_back(in_id);
+                        st.name = net.layers_[pit->second.layer]->d.name + " + " + st.name;
                     }
-                    if (rc != RT_OK) return fail(d.name + ": rt_conv3d_create failed (" + std::to_string(rc) + ")");
-                    conv3d_plans_.push_back(plan);
-                    st.workspace = rt_conv3d_workspace_size(plan, max_batch_);
-                    const int in_id = d.in[0]->id, out_id = out->id;
+                    // The plan is created after the layout pass below (it depends on the tensor layouts).
+                    conv_steps_.emplace_back(new ConvStep());
+                    ConvStep* cs = conv_steps_.back().get();
+                    cs->desc = cd; cs->in_id = in_id; cs->out_id = out->id; cs->skip_id = skip_id; cs->name = d.name;
                     if (skip_id >= 0) st.in.push_back(skip_id);
-                    st.out.push_back(out_id);
-                    st.run = [plan, in_id, out_id, skip_id](int batch, const std::function<void*(int)>& ptr, void* ws, cudaStream_t s) {
-                        return rt_conv3d_enqueue(plan, batch, ptr(in_id), skip_id >= 0 ? ptr(skip_id) : nullptr, ptr(out_id), ws, s);
+                    st.out.push_back(out->id);
+                    st.conv = cs;
+                    st.run = [cs](int batch, const std::function<void*(int)>& ptr, void* ws, cudaStream_t s) {
+                        return rt_conv3d_enqueue(cs->plan, batch, ptr(cs->in_id), cs->skip_id >= 0 ? ptr(cs->skip_id) : nullptr,
+                                                 ptr(cs->out_id), ws, s);
                     };
                     break;
                 }
+                // ---- Padding in front of a 3-D convolution: absorbed into the conv (virtual zero planes) --------------
+                if (fusion && op && op->kind == OpKind::kPadding) {
+                    const int nxt = soleConsumer(d.out[0]);
+                    const OpInfo* no = nxt >= 0 ? opOf(nxt) : nullptr;
+                    if (no && no->kind == OpKind::kConv3D) {
+                        absorbed_pad[nxt] = PadInfo{d.in[0]->id, op->pad_end_planes, li};
+                        continue;                                  // no step of its own
+                    }
+                }
+                // ---- cost volume / Transform: remember them, the layout pass may rewrite or drop them ------------------
+                if (fusion && op && op->kind == OpKind::kCostVolume && op->cv_type == redtail::tensorrt::CostVolumeType::kDefault &&
+                    op->data_type == DataType::kFLOAT) {
+                    st.costvol_c = d.in[0]->dims.d[0];
+                    st.costvol_h = d.in[0]->dims.d[1];
+                    st.costvol_w = d.in[0]->dims.d[2];
+                    st.costvol_d = op->max_disparity;
+                }
+                if (fusion && op && op->kind == OpKind::kTransform) st.is_transform = true;
                 // ---- generic plugin protocol ---------------------------------------------------------------------
                 std::vector<Dims> ind, outd;
                 for (auto* t : d.in) ind.push_back(t->dims);
@@ -734,7 +777,101 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
         }
         steps_.push_back(std::move(st));
     }
+    if (!assignLayoutsAndCreatePlans(fusion)) return false;
     return planMemory();
+}
+
+// Decides which activation tensors live in RT_LAYOUT_SPLIT16 (channels-last fp16 hi/lo, what the tcgen05 conv kernel
+// consumes and can produce) instead of dense fp32, then creates the convolution plans.
+// A tensor is split16 iff it is produced by a tensor-core conv step or by the concat cost volume, and every consumer is
+// a tensor-core conv step (as input, or as skip of a conv whose output is split16 too) -- possibly through
+// Transform{1,0,2,3} steps, which are no-ops on a channels-last tensor and are dropped.
+bool EngineImpl::assignLayoutsAndCreatePlans(bool fusion)
+{
+    const int ns = static_cast<int>(steps_.size());
+    const int nt = static_cast<int>(slots_.size());
+    std::vector<int> producer(nt, -1);
+    std::vector<std::vector<int>> consumers(nt);
+    for (int si = 0; si < ns; ++si) {
+        for (int id : steps_[si].out) producer[id] = si;
+        for (int id : steps_[si].in) consumers[id].push_back(si);
+    }
+    auto tcOk = [&](const ConvStep* cs, int in_layout, int out_layout) {
+        rt_conv3d_desc d = cs->desc;
+        d.in_layout = in_layout; d.out_layout = out_layout;
+        return rt_conv3d_tc_supported(&d) == 1;
+    };
+    std::vector<char> split(nt, 0);
+    const bool enable = fusion && getenv("REDTAIL_ENGINE_SPLIT16") == nullptr ? true : (fusion && getenv("REDTAIL_ENGINE_SPLIT16")[0] != '0');
+    if (enable) {
+        // optimistic start: every tensor produced by a capable step ...
+        for (int t = 0; t < nt; ++t) {
+            if (slots_[t].binding >= 0 || slots_[t].alias_of >= 0 || producer[t] < 0) continue;
+            const Step& ps = steps_[producer[t]];
+            const bool conv_prod = ps.conv && tcOk(ps.conv, RT_LAYOUT_DENSE, RT_LAYOUT_SPLIT16);
+            const bool cv_prod = ps.costvol_d > 0 && (2 * ps.costvol_c) % 8 == 0;
+            const bool tr_prod = ps.is_transform;              // decided through its input below
+            split[t] = (conv_prod || cv_prod || tr_prod) ? 1 : 0;
+        }
+        // ... then demote until every constraint holds.
+        for (bool changed = true; changed;) {
+            changed = false;
+            for (int t = 0; t < nt; ++t) {
+                if (!split[t]) continue;
+                bool ok = !consumers[t].empty();
+                const Step& ps = steps_[producer[t]];
+                if (ps.is_transform && !split[ps.in[0]]) ok = false;         // a transform only forwards a split16 tensor
+                for (int si : consumers[t]) {
+                    const Step& c = steps_[si];
+                    if (c.is_transform) { ok = ok && split[c.out[0]]; continue; }
+                    if (!c.conv) { ok = false; continue; }
+                    if (c.conv->in_id == t) ok = ok && tcOk(c.conv, RT_LAYOUT_SPLIT16, split[c.conv->out_id] ? RT_LAYOUT_SPLIT16 : RT_LAYOUT_DENSE);
+                    if (c.conv->skip_id == t) ok = ok && split[c.conv->out_id];   // skip shares the output's layout
+                }
+                if (!ok) { split[t] = 0; changed = true; }
+            }
+            // a conv with a dense skip cannot write split16
+            for (int si = 0; si < ns; ++si) {
+                const ConvStep* cs = steps_[si].conv;
+                if (cs && cs->skip_id >= 0 && split[cs->out_id] && !split[cs->skip_id]) { split[cs->out_id] = 0; changed = true; }
+            }
+        }
+    }
+    int nsplit = 0;
+    for (int si = 0; si < ns; ++si) {
+        Step& st = steps_[si];
+        if (st.is_transform && split[st.in[0]] && split[st.out[0]]) {       // no-op on channels-last data
+            slots_[st.out[0]].alias_of = st.in[0];
+            st.dropped = true;
+            continue;
+        }
+        if (st.costvol_d > 0 && split[st.out[0]]) {
+            const int l = st.in[0], r = st.in[1], o = st.out[0];
+            const int c = st.costvol_c, h = st.costvol_h, w = st.costvol_w, dd = st.costvol_d;
+            st.workspace = 0;
+            st.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                return rt_cost_volume_split16(ptr(l), ptr(r), ptr(o), batch, c, h, w, dd, s);
+            };
+        }
+        if (st.conv) {
+            ConvStep* cs = st.conv;
+            cs->desc.in_layout = split[cs->in_id] ? RT_LAYOUT_SPLIT16 : RT_LAYOUT_DENSE;
+            cs->desc.out_layout = split[cs->out_id] ? RT_LAYOUT_SPLIT16 : RT_LAYOUT_DENSE;
+            nsplit += split[cs->out_id];
+            int rc = rt_conv3d_create(&cs->desc, &cs->plan);
+            if (rc == RT_ERR_UNSUPPORTED && cs->desc.precision != RT_PREC_SIMT) {
+                logMsg(log_, ILogger::Severity::kWARNING, cs->name + ": shape not covered by the tcgen05 kernels, using the fp32 SIMT kernels.");
+                cs->desc.precision = RT_PREC_SIMT;
+                rc = rt_conv3d_create(&cs->desc, &cs->plan);
+            }
+            if (rc != RT_OK) return fail(cs->name + ": rt_conv3d_create failed (" + std::to_string(rc) + ")");
+            conv3d_plans_.push_back(cs->plan);
+            st.workspace = rt_conv3d_workspace_size(cs->plan, max_batch_);
+        }
+    }
+    steps_.erase(std::remove_if(steps_.begin(), steps_.end(), [](const Step& s) { return s.dropped; }), steps_.end());
+    logMsg(log_, ILogger::Severity::kINFO, "engine: " + std::to_string(nsplit) + " activation tensors kept in the split16 layout");
+    return true;
 }
 
 bool EngineImpl::planMemory()
