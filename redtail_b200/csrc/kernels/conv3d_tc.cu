@@ -257,8 +257,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         uint32_t lo_a = (st_addr >> 4) | (1u << 16);
                         uint32_t lo_l = ((st_addr + a_bytes) >> 4) | (1u << 16);
                         uint32_t lo_b = ((st_addr + (SPLIT ? 2u : 1u) * a_bytes) >> 4) | (1u << 16);
+                        const int nr = gr == 1 ? 1 : p.cls[jc.cls].taps[kb / ncb].nr;
                         if (elect_one_sync()) {
-                            for (int i = 0; i < gr; ++i) {                     // taps of the row group share the A box
+                            for (int i = 0; i < nr; ++i) {                     // taps of the row group share the A box
                                 uint32_t xa = lo_a + i * grp_a16, xl = lo_l + i * grp_a16, xb = lo_b + i * grp_b16;
                                 for (int kk = 0; kk < kc16; ++kk) {
                                     umma_f16(d0, desc_hi | xa, desc_hi | xb, idesc_full, (kb > kb0 || i > 0 || kk > 0) ? 1u : 0u);
@@ -571,12 +572,28 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     };
     struct Tile { int cls; int off[3]; };
     std::vector<Tile> tiles;
-    // Row groups (see TapEntry): stride-1 forward convs with 3 filter rows, when >= 3 pipeline stages still fit.
+    // Row groups (see TapEntry): the H shifts of a class are consecutive (3 filter rows of a stride-1 conv, 2 shifts of
+    // a merged-parity transposed conv); they share one A box when >= 3 pipeline stages still fit.  Needs in_s == 1.
     p.gr = 1;
-    if (!tr && d.r == 3 && d.stride[0] == 1 && d.stride[1] == 1 && d.stride[2] == 1 && !getenv("REDTAIL_TC_NOGROUP")) {
-        const int a_g = (p.th + 2) * p.tw * p.kc * 2;
-        const int b_g = (nb * p.kc * 2 + 1023) & ~1023;
-        if ((196 * 1024) / (a_g * (split ? 2 : 1) + 3 * b_g) >= 3) p.gr = 3;
+    if (p.in_s[0] == 1 && p.in_s[1] == 1 && p.in_s[2] == 1 && !getenv("REDTAIL_TC_NOGROUP")) {
+        int want = 1;
+        if (!tr) want = d.r;
+        else
+            for (int e = 0; e < (lmerge[1] ? 1 : d.stride[1]); ++e) {
+                int cnt = 0;
+                for (int off = -4; off <= 4; ++off) {
+                    bool any = false;
+                    for (int em = 0; em <= lmerge[1]; ++em) any = any || tap_of(1, lmerge[1] ? em : e, off) >= 0;
+                    cnt += any;
+                }
+                want = cnt > want ? cnt : want;
+            }
+        if (want > 3) want = 3;
+        for (; want > 1; --want) {
+            const int a_g = (p.th + want - 1) * p.tw * p.kc * 2;
+            const int b_g = (nb * p.kc * 2 + 1023) & ~1023;
+            if ((196 * 1024) / (a_g * (split ? 2 : 1) + want * b_g) >= 3) { p.gr = want; break; }
+        }
     }
     int job = 0, ci = 0;
     for (int ed = 0; ed < ncls[0]; ++ed)
@@ -604,8 +621,9 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
                             if (c.ntaps >= kMaxTaps || tiles.size() + p.gr > 255) { delete t; return RT_ERR_UNSUPPORTED; }
                             TapEntry te{};
                             te.dd = static_cast<int8_t>(od); te.dh = static_cast<int8_t>(offs[1][hi2]); te.dw = static_cast<int8_t>(ow);
-                            te.nr = static_cast<uint8_t>(p.gr);
-                            for (int g = 0; g < p.gr; ++g) {               // consecutive dh by construction (3 filter rows)
+                            const int nr = static_cast<int>(offs[1].size() - hi2) < p.gr ? static_cast<int>(offs[1].size() - hi2) : p.gr;
+                            te.nr = static_cast<uint8_t>(nr);
+                            for (int g = 0; g < nr; ++g) {                 // consecutive dh by construction
                                 te.widx[g] = static_cast<uint8_t>(tiles.size());
                                 tiles.push_back(Tile{ci, {od, offs[1][hi2 + g], ow}});
                             }
