@@ -207,6 +207,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- this engine has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION/INFO; stdout must carry exactly one JSON line.
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from redtail_b200 import StereoEngine, ops
@@ -294,10 +297,40 @@ def main():
                 "kernel": "3-D conv / transposed-conv stack (%d launches/step), algorithmic %.1f GFLOP/pair" % (n_conv, conv_stack_flops() / 1e9),
                 "peak_source": peaks["source"] + " cuBLAS bf16 (sustained)", "share_of_step": conv_ms / total_ms if total_ms else None,
                 "precision": os.environ.get("REDTAIL_CONV3D_PRECISION", "fp32") + " (" + ops.last_kernel() + ")"}
+    # DRAM traffic of the dominant kernels from the committed `ncu --set full` capture (profiles/r01_traffic.json).
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)
+    roofline["traffic"] = traffic.get("conv3d_stack_bytes_per_pair")
+    # Cost volume, as the engine runs it (written straight into the split16 layout conv3D_1 consumes) ...
     cv_gbs = COST_VOLUME_BYTES * B / (cv_ms * 1e-3) / 1e9 if cv_ms > 0 else 0.0
-    roofline_cv = {"bound": "hbm", "achieved": cv_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": cv_gbs / peaks["hbm_gbs"],
-                   "traffic": None, "kernel": "cost volume (dense [D,2C,H,W] fp32), algorithmic 1036.0 MB/pair",
-                   "peak_source": peaks["source"] + " copy", "share_of_step": cv_ms / total_ms if total_ms else None}
+    roofline_cv_engine = {"bound": "hbm", "achieved": cv_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": cv_gbs / peaks["hbm_gbs"],
+                          "traffic": traffic.get("cost_volume_split16_bytes"),
+                          "kernel": "cost_volume_split16 (fp16 hi/lo channels-last [D,H,W,2C]), algorithmic 1036.0 MB/pair",
+                          "peak_source": peaks["source"] + " copy", "share_of_step": cv_ms / total_ms if total_ms else None}
+    # ... and the plugin-faithful dense kernel (CostVolumePlugin::enqueue: TMA-staged, 128-bit stores, [D,2C,H,W] fp32),
+    # timed alone with CUDA events on the NVSmall shape (CostVolumePluginPerfTests.NVSmall, tests_main.cpp:938-958).
+    fl = torch.randn(1, 32, 161, 513, device="cuda")
+    fr = torch.randn(1, 32, 161, 513, device="cuda")
+    for _ in range(3):
+        cv = ops.cost_volume(fl, fr, MAX_DISP)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    c0.record()
+    for _ in range(reps):
+        ops.cost_volume(fl, fr, MAX_DISP)       # 1.0 GB written per launch >> L2
+    c1.record()
+    torch.cuda.synchronize()
+    dense_ms = c0.elapsed_time(c1) / reps
+    dense_gbs = COST_VOLUME_BYTES / (dense_ms * 1e-3) / 1e9
+    roofline_cv = {"bound": "hbm", "achieved": dense_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": dense_gbs / peaks["hbm_gbs"],
+                   "traffic": traffic.get("cost_volume_tma_bytes"), "ms_per_launch": dense_ms,
+                   "kernel": "cost_volume_tma_kernel (dense [D,2C,H,W] fp32 plugin layout), algorithmic 1036.0 MB/launch",
+                   "peak_source": peaks["source"] + " copy (burst)"}
+    del cv, fl, fr
 
     pairs = world * B * args.steps
     value = pairs / (ms * 1e-3)
@@ -316,6 +349,7 @@ def main():
         "clocks": sampler.summary(),
         "roofline": roofline,
         "roofline_cost_volume": roofline_cv,
+        "roofline_cost_volume_engine": roofline_cv_engine,
         "layer_ms": {k: round(v, 4) for k, v in acc.items()},
     }
     if world == 1 and not args.no_cpu_baseline:
