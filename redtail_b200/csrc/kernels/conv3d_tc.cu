@@ -75,7 +75,8 @@ struct TcParams {
     int split;               // 1: hi/lo operands (RT_PREC_FP32), 0: hi only
     int stages;
     int chunk_kb;            // K blocks accumulated in TMEM before the epilogue adds them up in fp32 registers
-    int gr;                  // taps per row group (1 or 3)
+    int gr;                  // taps per row group (1..3)
+    int mt;                  // M tiles (128 positions each, stacked along H) per job: they share the A halo and the weights
     int a_bytes, b_bytes, b_tx, stage_bytes;   // b_bytes: 1 KB-rounded slot, b_tx: bytes the weight TMA actually delivers
     int out_d, out_h, out_w; // output extent actually written
     long long out_sn, out_sc, out_sd;   // element strides of sample, channel, depth in the dense fp32 output
@@ -140,14 +141,14 @@ __device__ __forceinline__ JobCoord decode_job(const TcParams& p, int job) {
     const int tw_n = p.cls[c].tiles_w, th_n = p.cls[c].tiles_h;
     j.w0 = (r % tw_n) * p.tw;
     r /= tw_n;
-    j.h0 = (r % th_n) * p.th;
+    j.h0 = (r % th_n) * (p.th * p.mt);
     j.d = r / th_n;
     return j;
 }
 
 // Epilogue register budget: each of the 8 epilogue warps owns one TMEM lane quarter (warp_id % 4) and one half of the
 // output channels, i.e. CPH = cout_pad / 2 columns of D0 (and of D1 in split mode) per thread.
-template <int CPH, bool SPLIT>
+template <int CPH, bool SPLIT, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w, const __grid_constant__ TcParams p,
@@ -167,7 +168,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 
     constexpr int kCoutPad = 2 * CPH;
     constexpr int kAccCols = SPLIT ? 2 * kCoutPad : kCoutPad;   // TMEM columns of one accumulator buffer (= p.nb)
-    constexpr int kNumBuf = (512 / kAccCols) > 8 ? 8 : (512 / kAccCols);   // accumulator buffers the MMA warp may run ahead by
+    constexpr int kBufCols = MT * kAccCols;                     // one buffer = the accumulators of the MT tiles of a job
+    constexpr int kNumBuf = (512 / kBufCols) > 8 ? 8 : (512 / kBufCols);   // buffers the MMA warp may run ahead by
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -238,6 +240,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             const int kc16 = p.kc >> 4, stages = p.stages, chunk_kb = p.chunk_kb, ncb = p.ncb, gr = p.gr;
             const uint32_t grp_a16 = (static_cast<uint32_t>(p.tw) * pitch) >> 4;   // one patch row of A, in 16-byte units
             const uint32_t grp_b16 = static_cast<uint32_t>(p.b_bytes) >> 4;
+            const uint32_t tile_a16 = (static_cast<uint32_t>(kTileM) * pitch) >> 4;    // next M tile of the job (th patch rows down)
             int stage = 0;
             uint32_t phase = 0;
             int buf = 0;
@@ -249,7 +252,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     const int kb1 = min(nkb, kb0 + chunk_kb);
                     mbar_wait(&tmem_empty[buf], bphase ^ 1);                   // epilogue drained this buffer
                     tc_fence_after();
-                    const uint32_t d0 = tmem_base + static_cast<uint32_t>(buf * kAccCols);
+                    const uint32_t d0 = tmem_base + static_cast<uint32_t>(buf * kBufCols);
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
@@ -260,11 +263,16 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         const int nr = gr == 1 ? 1 : p.cls[jc.cls].taps[kb / ncb].nr;
                         if (elect_one_sync()) {
                             for (int i = 0; i < nr; ++i) {                     // taps of the row group share the A box
-                                uint32_t xa = lo_a + i * grp_a16, xl = lo_l + i * grp_a16, xb = lo_b + i * grp_b16;
-                                for (int kk = 0; kk < kc16; ++kk) {
-                                    umma_f16(d0, desc_hi | xa, desc_hi | xb, idesc_full, (kb > kb0 || i > 0 || kk > 0) ? 1u : 0u);
-                                    if (SPLIT) umma_f16(d0 + kCoutPad, desc_hi | xl, desc_hi | xb, idesc_half, 1u);
-                                    xa += 2; xl += 2; xb += 2;                 // +32 bytes = one K=16 slice inside the swizzle atom
+#pragma unroll
+                                for (int mt = 0; mt < MT; ++mt) {              // M tiles of the job share the weight tile
+                                    uint32_t xa = lo_a + i * grp_a16 + mt * tile_a16, xl = lo_l + i * grp_a16 + mt * tile_a16;
+                                    uint32_t xb = lo_b + i * grp_b16;
+                                    const uint32_t dt = d0 + mt * kAccCols;
+                                    for (int kk = 0; kk < kc16; ++kk) {
+                                        umma_f16(dt, desc_hi | xa, desc_hi | xb, idesc_full, (kb > kb0 || i > 0 || kk > 0) ? 1u : 0u);
+                                        if (SPLIT) umma_f16(dt + kCoutPad, desc_hi | xl, desc_hi | xb, idesc_half, 1u);
+                                        xa += 2; xl += 2; xb += 2;             // +32 bytes = one K=16 slice inside the swizzle atom
+                                    }
                                 }
                             }
                             umma_commit(&empty_bar[stage]);                    // slot free once these MMAs retire
@@ -292,29 +300,36 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             const JobCoord jc = decode_job(p, job);
             const ClassInfo& ci = p.cls[jc.cls];
             const int nkb = ci.ntaps * p.ncb;
-            float acc0[CPH];
-            float acc1[SPLIT ? CPH : 1];
+            float acc0[MT][CPH];
+            float acc1[MT][SPLIT ? CPH : 1];
 #pragma unroll
-            for (int k = 0; k < CPH; ++k) acc0[k] = 0.f;
-            if (SPLIT) {
+            for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-                for (int k = 0; k < CPH; ++k) acc1[k] = 0.f;
+                for (int k = 0; k < CPH; ++k) acc0[mt][k] = 0.f;
+                if (SPLIT) {
+#pragma unroll
+                    for (int k = 0; k < CPH; ++k) acc1[mt][k] = 0.f;
+                }
             }
             for (int kb0 = 0; kb0 < nkb; kb0 += chunk_kb) {
                 mbar_wait(&tmem_full[buf], bphase);
                 tc_fence_after();
-                const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * kAccCols + col0);
                 constexpr int LW = CPH >= 16 ? 16 : 8;   // columns per tcgen05.ld
 #pragma unroll
-                for (int c0 = 0; c0 < CPH; c0 += LW) {
-                    uint32_t v0[LW], v1[LW];
-                    tmem_ld<LW>(trow + c0, v0);
-                    if (SPLIT) tmem_ld<LW>(trow + kCoutPad + c0, v1);
-                    tmem_ld_wait();
+                for (int mt = 0; mt < MT; ++mt) {
+                    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                          static_cast<uint32_t>(buf * kBufCols + mt * kAccCols + col0);
 #pragma unroll
-                    for (int k = 0; k < LW; ++k) {
-                        acc0[c0 + k] += __uint_as_float(v0[k]);
-                        if (SPLIT) acc1[c0 + k] += __uint_as_float(v1[k]);
+                    for (int c0 = 0; c0 < CPH; c0 += LW) {
+                        uint32_t v0[LW], v1[LW];
+                        tmem_ld<LW>(trow + c0, v0);
+                        if (SPLIT) tmem_ld<LW>(trow + kCoutPad + c0, v1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < LW; ++k) {
+                            acc0[mt][c0 + k] += __uint_as_float(v0[k]);
+                            if (SPLIT) acc1[mt][c0 + k] += __uint_as_float(v1[k]);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -322,7 +337,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 if (lane == 0) mbar_arrive(&tmem_empty[buf]);
                 if (++buf == kNumBuf) { buf = 0; bphase ^= 1; }
             }
-            const int hi_ = jc.h0 + hl, wi_ = jc.w0 + wl;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+            const int hi_ = jc.h0 + mt * p.th + hl, wi_ = jc.w0 + wl;
             if (hi_ < ci.hc && wi_ < ci.wc) {
                 const int bd = jc.d * p.out_s[0] + ci.ed, bh = hi_ * p.out_s[1] + ci.eh, bw = wi_ * p.out_s[2] + ci.ew;
                 const long long rowbase = p.out_split
@@ -348,8 +365,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                             float v[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                v[j] = acc0[k0 + j];
-                                if (SPLIT) v[j] = fmaf(acc1[k0 + j], 1.f / 2048.f, v[j]);
+                                v[j] = acc0[mt][k0 + j];
+                                if (SPLIT) v[j] = fmaf(acc1[mt][k0 + j], 1.f / 2048.f, v[j]);
                                 v[j] += s_bias[c0.ch + j];
                             }
                             if (skip) {
@@ -392,8 +409,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         if (idx[j] >= 0) {
-                            float val = acc0[k0 + j];
-                            if (SPLIT) val = fmaf(acc1[k0 + j], 1.f / 2048.f, val);
+                            float val = acc0[mt][k0 + j];
+                            if (SPLIT) val = fmaf(acc1[mt][k0 + j], 1.f / 2048.f, val);
                             val += s_bias[ch[j]] + sk[j];
                             if (p.fuse_elu) val = elu1(val);
                             out[idx[j]] = val;
@@ -401,6 +418,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     }
                 }
             }
+            }   // mt
         }
     }
     tc_fence_before();
@@ -595,6 +613,14 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
             if ((196 * 1024) / (a_g * (split ? 2 : 1) + want * b_g) >= 3) { p.gr = want; break; }
         }
     }
+    // Two H-stacked M tiles per job (forward convs with a row group, narrow N): the second tile reuses the weight tiles
+    // and shares the 2 halo rows of the A box -- 25 % less L2 -> SM traffic on the L2-bound 32-channel layers.
+    p.mt = 1;
+    if (!tr && p.gr == 3 && cout_pad <= 32 && cls_h >= 2 * p.th && !getenv("REDTAIL_TC_MT1")) {
+        const int a_g = (2 * p.th + p.gr - 1) * p.tw * p.kc * 2;
+        const int b_g = (nb * p.kc * 2 + 1023) & ~1023;
+        if ((196 * 1024) / (a_g * (split ? 2 : 1) + p.gr * b_g) >= 2) p.mt = 2;
+    }
     int job = 0, ci = 0;
     for (int ed = 0; ed < ncls[0]; ++ed)
         for (int eh = 0; eh < ncls[1]; ++eh)
@@ -603,7 +629,7 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
                 c.ed = ed; c.eh = eh; c.ew = ew;
                 const int e[3] = {ed, eh, ew};
                 c.dc = lattice(0, ed); c.hc = lattice(1, eh); c.wc = lattice(2, ew);
-                c.tiles_h = (c.hc + p.th - 1) / p.th; c.tiles_w = (c.wc + p.tw - 1) / p.tw;
+                c.tiles_h = (c.hc + p.th * p.mt - 1) / (p.th * p.mt); c.tiles_w = (c.wc + p.tw - 1) / p.tw;
                 c.job_begin = job;
                 job += c.dc * c.tiles_h * c.tiles_w;
                 c.ntaps = 0;
@@ -702,7 +728,7 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
         if (rc != 0) { cudaFree(t->w_dev); delete t; return rc > 0 ? rc : RT_ERR_UNSUPPORTED; }
     }
     // Shared-memory budget.
-    p.a_bytes = (p.th + p.gr - 1) * p.tw * p.kc * 2;
+    p.a_bytes = (p.th * p.mt + p.gr - 1) * p.tw * p.kc * 2;
     p.b_tx = nb * p.kc * 2;
     p.b_bytes = (p.b_tx + 1023) & ~1023;
     p.stage_bytes = p.a_bytes * (split ? 2 : 1) + p.gr * p.b_bytes;
@@ -770,7 +796,7 @@ int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const f
                                 static_cast<uint64_t>(t->cin) * 2 * t->in_w * t->in_h,
                                 static_cast<uint64_t>(t->in_elems) * 4};          // sample stride: hi + lo planes
         const uint32_t box[5] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.tw * p.in_s[2]),
-                                 static_cast<uint32_t>((p.th + p.gr - 1) * p.in_s[1]), 1u, 1u};
+                                 static_cast<uint32_t>((p.th * p.mt + p.gr - 1) * p.in_s[1]), 1u, 1u};
         const uint32_t es[5] = {1u, static_cast<uint32_t>(p.in_s[2]), static_cast<uint32_t>(p.in_s[1]), 1u, 1u};
         const CUtensorMapSwizzle swz = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
         int rc = make_tensor_map(&ma_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, hi, dims, st, box, es, swz);
@@ -781,20 +807,26 @@ int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const f
     // 3. main kernel
     int grid = num_sms();
     if (grid > p.njobs) grid = p.njobs;
-#define RT_LAUNCH_UMMA(CPH, SPL)                                                                                      \
+#define RT_LAUNCH_UMMA(CPH, SPL, MTT)                                                                                    \
     do {                                                                                                              \
         static bool attr_set = false;                                                                                 \
         if (!attr_set) {                                                                                              \
-            RT_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<CPH, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            RT_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<CPH, SPL, MTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
             attr_set = true;                                                                                          \
         }                                                                                                             \
-        conv3d_umma_kernel<CPH, SPL><<<grid, kThreads, t->smem_bytes, s>>>(ma_hi, ma_lo, t->map_w, p, plan->bias, t->d_cols, skip, y); \
+        conv3d_umma_kernel<CPH, SPL, MTT><<<grid, kThreads, t->smem_bytes, s>>>(ma_hi, ma_lo, t->map_w, p, plan->bias, t->d_cols, skip, y); \
     } while (0)
     switch (p.cout_pad) {
-        case 16:  if (p.split) RT_LAUNCH_UMMA(8, true);  else RT_LAUNCH_UMMA(8, false);  break;
-        case 32:  if (p.split) RT_LAUNCH_UMMA(16, true); else RT_LAUNCH_UMMA(16, false); break;
-        case 64:  if (p.split) RT_LAUNCH_UMMA(32, true); else RT_LAUNCH_UMMA(32, false); break;
-        case 128: if (p.split) RT_LAUNCH_UMMA(64, true); else RT_LAUNCH_UMMA(64, false); break;
+        case 16:
+            if (p.mt == 2) { if (p.split) RT_LAUNCH_UMMA(8, true, 2); else RT_LAUNCH_UMMA(8, false, 2); }
+            else { if (p.split) RT_LAUNCH_UMMA(8, true, 1); else RT_LAUNCH_UMMA(8, false, 1); }
+            break;
+        case 32:
+            if (p.mt == 2) { if (p.split) RT_LAUNCH_UMMA(16, true, 2); else RT_LAUNCH_UMMA(16, false, 2); }
+            else { if (p.split) RT_LAUNCH_UMMA(16, true, 1); else RT_LAUNCH_UMMA(16, false, 1); }
+            break;
+        case 64:  if (p.split) RT_LAUNCH_UMMA(32, true, 1); else RT_LAUNCH_UMMA(32, false, 1); break;
+        case 128: if (p.split) RT_LAUNCH_UMMA(64, true, 1); else RT_LAUNCH_UMMA(64, false, 1); break;
         default: return RT_ERR_UNSUPPORTED;
     }
 #undef RT_LAUNCH_UMMA
