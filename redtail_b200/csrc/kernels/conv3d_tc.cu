@@ -591,7 +591,7 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     struct Tile { int cls; int off[3]; };
     std::vector<Tile> tiles;
     // Row groups (see TapEntry): the H shifts of a class are consecutive (3 filter rows of a stride-1 conv, 2 shifts of
-    // a merged-parity transposed conv); they share one A box when >= 3 pipeline stages still fit.  Needs in_s == 1.
+    // a merged-parity transposed conv); they share one A box when >= 2 pipeline stages still fit.  Needs in_s == 1.
     p.gr = 1;
     if (p.in_s[0] == 1 && p.in_s[1] == 1 && p.in_s[2] == 1 && !getenv("REDTAIL_TC_NOGROUP")) {
         int want = 1;
@@ -607,10 +607,12 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
                 want = cnt > want ? cnt : want;
             }
         if (want > 3) want = 3;
+        int min_stages = 2;     // measured: a 2-stage ring with 1/3 of the A traffic beats a deeper per-tap ring (conv3D_4/5: -25 %)
+        if (const char* e = getenv("REDTAIL_TC_MINSTAGES")) min_stages = atoi(e) > 0 ? atoi(e) : 2;
         for (; want > 1; --want) {
             const int a_g = (p.th + want - 1) * p.tw * p.kc * 2;
             const int b_g = (nb * p.kc * 2 + 1023) & ~1023;
-            if ((196 * 1024) / (a_g * (split ? 2 : 1) + want * b_g) >= 3) { p.gr = want; break; }
+            if ((196 * 1024) / (a_g * (split ? 2 : 1) + want * b_g) >= min_stages) { p.gr = want; break; }
         }
     }
     // Two H-stacked M tiles per job (forward convs with a row group, narrow N): the second tile reuses the weight tiles
