@@ -10,8 +10,14 @@
 // time.  Activations are first re-laid out channels-last as fp16 ([N][D][H][W][C], see pack kernel) so that the A
 // operand of a tap is a plain TMA box [tw x th x KC] at a shifted coordinate -- zero padding (D, H and W) is TMA
 // out-of-bounds fill, never materialised; stride-2 convolutions use TMA traversal strides.  A transposed convolution
-// of stride s is s^3 independent "parity classes", each a stride-1 convolution over a subset of the taps whose
-// outputs are scattered with stride s by the epilogue.
+// of stride s is computed as a sub-pixel convolution: its s^3 output parities ride along GEMM-N (merged while N <= 128,
+// the rest are separate classes), A tiles are loaded once per SHIFT instead of once per tap, and the epilogue does the
+// depth-to-space scatter.
+//
+// L2 -> SM traffic (what bounds the 32-channel layers) is cut three ways: (1) row groups -- the 3 filter rows of a
+// stride-1 conv read one TMA box that is 2 patch rows taller, at 1 KB-aligned row offsets; (2) two H-stacked M tiles per
+// job share those halo rows and the weight tiles; (3) activations between two convolutions stay in RT_LAYOUT_SPLIT16
+// (channels-last fp16 hi/lo planes written by the epilogue), so no re-layout / Transform / Padding pass ever runs.
 //
 // Numerics (RT_PREC_FP32): the fp32 tolerance of the plugin path (1e-3 px disparity after 11 chained layers) cannot be
 // held by a single fp16/bf16/tf32 product.  Every operand x is split as x = hi + 2^-11 * lo with hi = fp16(x),
@@ -20,9 +26,14 @@
 // The first two products share one MMA of N = 2*Cout ([W_hi ; W_lo] stacked along N), so A_hi is read once.
 // RT_PREC_FP16 issues only the hi*hi product (the reference's fp16 configs, 1e-2 tolerance).
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 epilogue (TMEM -> registers ->
-// bias / skip / ELU -> coalesced fp32 stores).  Persistent grid (one CTA per SM), static round-robin tile schedule,
-// smem ring of kStages operand stages, two TMEM accumulator buffers so the epilogue of tile i overlaps the MMAs of i+1.
+// The tensor core accumulates in fp32 with TRUNCATION (measured: a 108-step chain drifts NVSmall's disparity by 6e-3 px),
+// so TMEM chains are kept to ~8-12 K-steps ("chunk") and the epilogue warps add every chunk into fp32 registers with
+// round-to-nearest while the next chunk runs in another TMEM buffer.
+//
+// CTA = 10 warps: warp 0 TMA producer, warp 1 MMA issuer (elect.sync; + TMEM allocation, all 512 columns = 2..8
+// accumulator buffers), warps 2-9 epilogue (tcgen05.ld -> registers -> bias / skip / ELU -> dense fp32 or split16 stores;
+// each warp owns one TMEM lane quarter and one half of the columns).  Persistent grid (one CTA per SM), static round-robin
+// tile schedule, 2..8-stage smem operand ring.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -484,10 +495,14 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     int lmerge[3] = {0, 0, 0};
     if (tr) {
         int ncol = cpc;
+        // Merged columns are capped at 64: N = 128 (x2 in split mode) leaves only two TMEM buffers and a 256-column
+        // epilogue per chunk, which measured slower (deconv3D_2: 0.95 ms at 128 vs 0.73 ms at 64).
+        int max_n = 64;
+        if (const char* e = getenv("REDTAIL_TC_MAXN")) max_n = atoi(e) >= 16 ? atoi(e) : 64;
         const int order[3] = {2, 1, 0};                  // merge W first (adjacent outputs), then H, then D
         for (int oi = 0; oi < 3; ++oi) {
             const int i = order[oi];
-            if (d.stride[i] == 2 && ncol * 2 <= 128) { lmerge[i] = 1; ncol *= 2; }
+            if (d.stride[i] == 2 && ncol * 2 <= max_n) { lmerge[i] = 1; ncol *= 2; }
         }
     }
     const int ncols = cpc << (lmerge[0] + lmerge[1] + lmerge[2]);
