@@ -809,7 +809,7 @@ bool EngineImpl::assignLayoutsAndCreatePlans(bool fusion)
             if (slots_[t].binding >= 0 || slots_[t].alias_of >= 0 || producer[t] < 0) continue;
             const Step& ps = steps_[producer[t]];
             const bool conv_prod = ps.conv && tcOk(ps.conv, RT_LAYOUT_DENSE, RT_LAYOUT_SPLIT16);
-            const bool cv_prod = ps.costvol_d > 0 && (2 * ps.costvol_c) % 8 == 0;
+            const bool cv_prod = ps.costvol_d > 0 && ps.costvol_c % 8 == 0;
             const bool tr_prod = ps.is_transform;              // decided through its input below
             split[t] = (conv_prod || cv_prod || tr_prod) ? 1 : 0;
         }

@@ -633,7 +633,7 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     // Two H-stacked M tiles per job (forward convs with a row group, narrow N): the second tile reuses the weight tiles
     // and shares the 2 halo rows of the A box -- 25 % less L2 -> SM traffic on the L2-bound 32-channel layers.
     p.mt = 1;
-    if (!tr && p.gr == 3 && cout_pad <= 32 && cls_h >= 2 * p.th && !getenv("REDTAIL_TC_MT1")) {
+    if (p.gr >= 2 && cout_pad <= 32 && cls_h >= 2 * p.th && !getenv("REDTAIL_TC_MT1")) {
         const int a_g = (2 * p.th + p.gr - 1) * p.tw * p.kc * 2;
         const int b_g = (nb * p.kc * 2 + 1023) & ~1023;
         if ((196 * 1024) / (a_g * (split ? 2 : 1) + p.gr * b_g) >= 2) p.mt = 2;

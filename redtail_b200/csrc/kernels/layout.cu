@@ -24,47 +24,73 @@ __device__ __forceinline__ void split_store8(const float (&v)[8], __half* hi, __
 }
 
 // One CTA: 64 consecutive x of one (n, y) row, all 2C channels, all D disparities.
-// smem: left [C][64], right [C][64 + D - 1] (x - D + 1 .. x + 63), fp32.
+// The fp32 -> (hi, lo) split and the channel transpose are done ONCE per source element into shared memory, already in
+// the output's 16-byte channel-vector order; the D output runs are then plain LDS.128 -> STG.128 copies (the right half
+// at a per-disparity pixel shift), so the kernel is bound by HBM writes, not by conversion instructions.
+//   smem (uint4 = 8 fp16 channels):  L_hi/L_lo [64][C/8],  R_hi/R_lo [64 + D - 1][C/8]
 __global__ void __launch_bounds__(256)
 cost_volume_split16_kernel(const float* __restrict__ left, const float* __restrict__ right, __half* __restrict__ out,
                            int c, int h, int w, int disp) {
-    extern __shared__ float sm[];
+    extern __shared__ uint4 smv[];
+    const int g4 = c >> 3;                                   // channel vectors per side
     const int rw = 64 + disp - 1;
-    float* sl = sm;                 // [c][65]
-    float* sr = sm + c * 65;        // [c][rw + 1]
+    uint4* l_hi = smv;
+    uint4* l_lo = l_hi + 64 * g4;
+    uint4* r_hi = l_lo + 64 * g4;
+    uint4* r_lo = r_hi + rw * g4;
     const int x0 = blockIdx.x * 64, y = blockIdx.y, n = blockIdx.z;
     const long long hw = static_cast<long long>(h) * w;
     const float* lp = left + static_cast<long long>(n) * c * hw + static_cast<long long>(y) * w;
     const float* rp = right + static_cast<long long>(n) * c * hw + static_cast<long long>(y) * w;
-    for (int i = threadIdx.x; i < c * 64; i += 256) {
-        const int ch = i >> 6, x = i & 63;
-        sl[ch * 65 + x] = (x0 + x < w) ? __ldg(lp + ch * hw + x0 + x) : 0.f;
-    }
-    for (int i = threadIdx.x; i < c * rw; i += 256) {
-        const int ch = i / rw, j = i % rw;
-        const int x = x0 - (disp - 1) + j;
-        sr[ch * (rw + 1) + j] = (x >= 0 && x < w) ? __ldg(rp + ch * hw + x) : 0.f;
+    // stage + split: item = (pixel j, channel vector g); consecutive threads take consecutive pixels (coalesced reads)
+    for (int i = threadIdx.x; i < (64 + rw) * g4; i += 256) {
+        const bool is_r = i >= 64 * g4;
+        const int k = is_r ? i - 64 * g4 : i;
+        const int span = is_r ? rw : 64;
+        const int g = k / span, j = k % span;
+        const int x = is_r ? x0 - (disp - 1) + j : x0 + j;
+        const float* src = (is_r ? rp : lp) + static_cast<long long>(g) * 8 * hw + x;
+        __align__(16) __half hv[8];
+        __align__(16) __half lv[8];
+        const bool inb = x >= 0 && x < w;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float v = inb ? __ldg(src + q * hw) : 0.f;
+            v = fminf(fmaxf(v, -65504.f), 65504.f);
+            const __half hh = __float2half_rn(v);
+            hv[q] = hh;
+            lv[q] = __float2half_rn((v - __half2float(hh)) * 2048.f);
+        }
+        (is_r ? r_hi : l_hi)[j * g4 + g] = *reinterpret_cast<const uint4*>(hv);
+        (is_r ? r_lo : l_lo)[j * g4 + g] = *reinterpret_cast<const uint4*>(lv);
     }
     __syncthreads();
-    const int c2 = 2 * c, groups = c2 >> 3;
+    const int c2 = 2 * c, groups = 2 * g4;
     const long long plane = static_cast<long long>(disp) * hw * c2;          // elements of one fp16 plane
     __half* hi = out + static_cast<long long>(n) * 2 * plane;
     __half* lo = hi + plane;
     const int items = 64 * groups;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     for (int d = 0; d < disp; ++d) {
         const long long row = ((static_cast<long long>(d) * h + y) * w + x0) * c2;
         for (int i = threadIdx.x; i < items; i += 256) {
             const int x = i / groups, g = i % groups;
             if (x0 + x >= w) continue;
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int ch = g * 8 + k;
-                if (ch < c) v[k] = sl[ch * 65 + x];
-                else v[k] = (x0 + x >= d) ? sr[(ch - c) * (rw + 1) + x + (disp - 1) - d] : 0.f;
+            uint4 vh, vl;
+            if (g < g4) {
+                vh = l_hi[x * g4 + g];
+                vl = l_lo[x * g4 + g];
+            } else if (x0 + x >= d) {
+                const int j = x + (disp - 1) - d;
+                vh = r_hi[j * g4 + g - g4];
+                vl = r_lo[j * g4 + g - g4];
+            } else {
+                vh = zero;
+                vl = zero;
             }
             const long long o = row + static_cast<long long>(x) * c2 + g * 8;
-            split_store8(v, hi + o, lo + o);
+            *reinterpret_cast<uint4*>(hi + o) = vh;
+            *reinterpret_cast<uint4*>(lo + o) = vl;
         }
     }
 }
@@ -135,7 +161,8 @@ int rt_cost_volume_split16(const void* left, const void* right, void* out, int n
     if ((2 * c) % 8 != 0) return RT_ERR_UNSUPPORTED;
     if (n == 0) return RT_OK;
     if (h > 65535 || n > 65535) return RT_ERR_UNSUPPORTED;
-    const size_t smem = (static_cast<size_t>(c) * 65 + static_cast<size_t>(c) * (64 + max_disp)) * sizeof(float);
+    if (c % 8 != 0) return RT_ERR_UNSUPPORTED;
+    const size_t smem = static_cast<size_t>(c / 8) * (64 + 64 + max_disp - 1) * 2 * sizeof(uint4);
     if (smem > 200 * 1024) return RT_ERR_UNSUPPORTED;
     if (smem > 48 * 1024) RT_CUDA(cudaFuncSetAttribute(cost_volume_split16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     dim3 grid((w + 63) / 64, h, n);
