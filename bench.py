@@ -56,12 +56,13 @@ def synthetic_pairs(batch, seed=1234):
     return np.stack(ls), np.stack(rs)
 
 
-def conv_stack_flops():
+def conv_stack_flops(with_conv1=True):
     """Algorithmic FLOPs of the eleven 3-D conv / transposed-conv layers per NVSmall pair:
-    conv: 2*Cout*27*Cin*Do*Ho*Wo ; transposed: 2*Cin*Cout*27*Di*Hi*Wi."""
+    conv: 2*Cout*27*Cin*Do*Ho*Wo ; transposed: 2*Cin*Cout*27*Di*Hi*Wi.
+    with_conv1=False leaves out conv3D_1 (438.4 GFLOP) for engines that run cost_vol+conv3D_1 in the separable form."""
     h, w, d = 161, 513, MAX_DISP
     f = 0.0
-    f += 2 * 32 * 27 * 64 * d * h * w + 2 * 32 * 27 * 32 * d * h * w                        # conv3D_1, 2
+    f += (2 * 32 * 27 * 64 * d * h * w if with_conv1 else 0) + 2 * 32 * 27 * 32 * d * h * w   # conv3D_1, 2
     d2, h2, w2 = d // 2, 81, 257
     f += 2 * 64 * 27 * 32 * d2 * h2 * w2 + 2 * (2 * 64 * 27 * 64 * d2 * h2 * w2)            # 3ds, 4, 5
     d3, h3, w3 = d2 // 2, 41, 129
@@ -289,12 +290,16 @@ def main():
     conv_ms = sum(t for n, t in acc.items() if n.startswith("conv3D_") or n.startswith("deconv3D_"))
     n_conv = sum(1 for n in acc if n.startswith("conv3D_") or n.startswith("deconv3D_"))
     cv_ms = sum(t for n, t in acc.items() if n.startswith("cost_vol"))
+    # cost_vol + conv3D_1 run as ONE step in the separable form (rt_costvol_conv3d_*): it is HBM-bound and reported on its own.
+    cv_fused = any(n.startswith("cost_vol") and "conv3D_1" in n for n in acc)
     total_ms = sum(acc.values())
-    flops = conv_stack_flops() * B
+    stack_flops = conv_stack_flops(with_conv1=not cv_fused)
+    flops = stack_flops * B
     achieved_tf = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved_tf / peaks["tflops_sustained"], "traffic": None,
-                "kernel": "3-D conv / transposed-conv stack (%d launches/step), algorithmic %.1f GFLOP/pair" % (n_conv, conv_stack_flops() / 1e9),
+                "kernel": "3-D conv / transposed-conv stack (%d launches/step), algorithmic %.1f GFLOP/pair" % (n_conv, stack_flops / 1e9) +
+                          (" (conv3D_1's 438.4 GFLOP are not executed: cost_vol+conv3D_1 run in the separable form, see roofline_cost_volume_engine)" if cv_fused else ""),
                 "peak_source": peaks["source"] + " cuBLAS bf16 (sustained)", "share_of_step": conv_ms / total_ms if total_ms else None,
                 "precision": os.environ.get("REDTAIL_CONV3D_PRECISION", "fp32") + " (" + ops.last_kernel() + ")"}
     # DRAM traffic of the dominant kernels from the committed `ncu --set full` capture (profiles/r01_traffic.json).
@@ -305,10 +310,19 @@ def main():
             traffic = json.load(f)
     roofline["traffic"] = traffic.get("conv3d_stack_bytes_per_pair")
     # Cost volume, as the engine runs it (written straight into the split16 layout conv3D_1 consumes) ...
-    cv_gbs = COST_VOLUME_BYTES * B / (cv_ms * 1e-3) / 1e9 if cv_ms > 0 else 0.0
+    if cv_fused:
+        # algorithmic bytes of the fused step: read the two feature maps, write conv3D_1's output once (fp16 hi+lo = 4 B/elt)
+        cv_bytes = (2 * 32 * 161 * 513 + MAX_DISP * 32 * 161 * 513) * 4
+        cv_kernel = ("cost_vol+conv3D_1 separable step (2x conv2d 32->96 on tcgen05 + edge + combine pass writing [D,H,W,32] hi/lo), "
+                     "algorithmic %.1f MB/pair" % (cv_bytes / 1e6))
+        cv_traffic = traffic.get("costvol_conv1_bytes")
+    else:
+        cv_bytes = COST_VOLUME_BYTES
+        cv_kernel = "cost_volume_split16 (fp16 hi/lo channels-last [D,H,W,2C]), algorithmic 1036.0 MB/pair"
+        cv_traffic = traffic.get("cost_volume_split16_bytes")
+    cv_gbs = cv_bytes * B / (cv_ms * 1e-3) / 1e9 if cv_ms > 0 else 0.0
     roofline_cv_engine = {"bound": "hbm", "achieved": cv_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": cv_gbs / peaks["hbm_gbs"],
-                          "traffic": traffic.get("cost_volume_split16_bytes"),
-                          "kernel": "cost_volume_split16 (fp16 hi/lo channels-last [D,H,W,2C]), algorithmic 1036.0 MB/pair",
+                          "traffic": cv_traffic, "kernel": cv_kernel, "ms_per_step": cv_ms,
                           "peak_source": peaks["source"] + " copy", "share_of_step": cv_ms / total_ms if total_ms else None}
     # ... and the plugin-faithful dense kernel (CostVolumePlugin::enqueue: TMA-staged, 128-bit stores, [D,2C,H,W] fp32),
     # timed alone with CUDA events on the NVSmall shape (CostVolumePluginPerfTests.NVSmall, tests_main.cpp:938-958).
@@ -332,6 +346,27 @@ def main():
                    "peak_source": peaks["source"] + " copy (burst)"}
     del cv, fl, fr
 
+    # The same engine with the cost volume materialised and conv3D_1 run as a 3-D convolution (REDTAIL_ENGINE_CVCONV=0),
+    # i.e. every reference layer executed literally: reported beside `value` so the effect of the separable form is visible.
+    literal = None
+    if cv_fused and world == 1:
+        os.environ["REDTAIL_ENGINE_CVCONV"] = "0"
+        eng2 = StereoEngine("nvsmall", H, W, WEIGHTS, max_batch=B)
+        del os.environ["REDTAIL_ENGINE_CVCONV"]
+        for _ in range(3):
+            eng2(d_left, d_right, out=d_disp)
+        torch.cuda.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(args.steps):
+            eng2(d_left, d_right, out=d_disp)
+        l1.record()
+        torch.cuda.synchronize()
+        lms = l0.elapsed_time(l1) / args.steps
+        literal = {"value": B / (lms * 1e-3), "unit": "stereo pairs/s", "ms_per_step": lms,
+                   "what": "REDTAIL_ENGINE_CVCONV=0: 1.0 GB cost volume written, conv3D_1 as a 438 GFLOP tcgen05 3-D convolution"}
+        del eng2
+
     pairs = world * B * args.steps
     value = pairs / (ms * 1e-3)
     out = {
@@ -341,6 +376,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "NVSmall 1025x321 fp32 batch=%d per GPU (BASELINE configs[1]): 2-D towers + cost volume D=48 + 11-layer 3-D conv stack + soft-argmin, reference's trained weights" % B,
                    "pairs_per_step": world * B, "parallelism": "dp%d (independent pairs, NCCL all-gather of disparity maps)" % world,
+                   "costvol_conv1": "separable (exact algebra, volume never materialised)" if cv_fused else "materialised",
                    "l2": "per-step working set (1.0 GB cost volume + 0.5 GB activations per layer) >> 126 MB L2; no explicit flush",
                    "vs_baseline_ref": "450 ms/pair TensorRT fp32 on Titan Xp (stereoDNN/README.md:28)"},
         "e2e": {"value": pairs / e2e_s, "unit": "stereo pairs/s", "h2d_bytes_per_step": int(2 * B * 3 * H * W * 4),
@@ -352,6 +388,8 @@ def main():
         "roofline_cost_volume_engine": roofline_cv_engine,
         "layer_ms": {k: round(v, 4) for k, v in acc.items()},
     }
+    if literal:
+        out["literal_layers"] = literal
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
     print(json.dumps(out))

@@ -126,6 +126,34 @@ size_t rt_conv3d_workspace_size(const rt_conv3d_plan* plan, int max_batch);
 int  rt_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const void* x, const void* skip, void* y,
                        void* workspace, void* stream);
 
+/* ---- fused CostVolume(kDefault) -> Conv3D 3x3x3 / stride 1 / pad 1 [-> Transform{1,0,2,3}] [-> ELU] ------------------
+ * Replaces the pair cost_volume_plugin.cpp:122-139 + conv3d_plugin.cpp:186-279 when the engine sees them back to back
+ * (SURVEY.md section 8, row N3).  The cost volume cv[d, 0:c] = L, cv[d, c:2c, y, x] = R[y, x-d] is a broadcast / shift of
+ * two 2-D maps, so the 3-D convolution over it separates exactly:
+ *     out[k,d,y,x] = b[k] + sum_v A_v[k,y,x] + sum_v C_v[k,y,x-(d+v-1)]          (v = filter plane, d+v-1 inside [0,D))
+ * with A_v = conv2d(L, W[:,v,0:c]), C_v = conv2d(R, W[:,v,c:2c]) (3x3, pad 1), minus the dw=+1 filter column at x = w-1
+ * (the volume ends there, the shifted image does not).  Neither the 1 GB volume nor the 438 GFLOP 3-D convolution are
+ * executed; results agree with the unfused pair to fp32 rounding.                                                        */
+typedef struct rt_cvconv_plan rt_cvconv_plan;
+typedef struct {
+    int c, h, w;             /* left/right feature maps, dense fp32 [n,c,h,w]                                  */
+    int max_disp;            /* D planes of the (never materialised) cost volume [D,2c,h,w]                    */
+    int k;                   /* conv outputs; weights KVCRS [k,3,2c,3,3]                                       */
+    int weights_dtype;       /* RT_F32 | RT_F16 (host arrays)                                                  */
+    const void* weights;
+    const void* bias;        /* host, k elements, or NULL                                                      */
+    int precision;           /* RT_PREC_* of the two inner 2-D convolutions                                    */
+    int fuse_elu;
+    int out_transposed;      /* dense output only: 1 -> [D,K,H,W] (Transform fused), 0 -> [K,D,H,W]            */
+    int out_layout;          /* RT_LAYOUT_DENSE | RT_LAYOUT_SPLIT16 ([n][hi|lo][D][h][w][k], k % 8 == 0)        */
+} rt_costvol_conv3d_desc;
+int  rt_costvol_conv3d_supported(const rt_costvol_conv3d_desc* desc);          /* 1 / 0, no allocation */
+int  rt_costvol_conv3d_create(const rt_costvol_conv3d_desc* desc, rt_cvconv_plan** plan);
+void rt_costvol_conv3d_destroy(rt_cvconv_plan* plan);
+size_t rt_costvol_conv3d_workspace_size(const rt_cvconv_plan* plan, int max_batch);
+int  rt_costvol_conv3d_enqueue(const rt_cvconv_plan* plan, int n, const void* left, const void* right, void* y,
+                               void* workspace, void* stream);
+
 /* ---- 2-D convolution / deconvolution (TensorRT-native layers of the builders) ------------------------ */
 typedef struct rt_conv2d_plan rt_conv2d_plan;
 typedef struct {

@@ -30,6 +30,12 @@ class Conv2dDesc(C.Structure):
                 ("weights_dtype", C.c_int), ("weights", C.c_void_p), ("bias", C.c_void_p), ("fuse_elu", C.c_int)]
 
 
+class CostvolConv3dDesc(C.Structure):
+    _fields_ = [("c", C.c_int), ("h", C.c_int), ("w", C.c_int), ("max_disp", C.c_int), ("k", C.c_int),
+                ("weights_dtype", C.c_int), ("weights", C.c_void_p), ("bias", C.c_void_p), ("precision", C.c_int),
+                ("fuse_elu", C.c_int), ("out_transposed", C.c_int), ("out_layout", C.c_int)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> (restype, argtypes): the complete export list of include/redtail_b200.h
@@ -57,6 +63,11 @@ KERNEL_API = {
     "rt_split16_to_dense": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "rt_conv3d_workspace_size": (C.c_size_t, [_P, _I]),
     "rt_conv3d_enqueue": (_I, [_P, _I, _P, _P, _P, _P, _P]),
+    "rt_costvol_conv3d_supported": (_I, [C.POINTER(CostvolConv3dDesc)]),
+    "rt_costvol_conv3d_create": (_I, [C.POINTER(CostvolConv3dDesc), C.POINTER(_P)]),
+    "rt_costvol_conv3d_destroy": (None, [_P]),
+    "rt_costvol_conv3d_workspace_size": (C.c_size_t, [_P, _I]),
+    "rt_costvol_conv3d_enqueue": (_I, [_P, _I, _P, _P, _P, _P, _P]),
     "rt_conv2d_create": (_I, [C.POINTER(Conv2dDesc), C.POINTER(_P)]),
     "rt_conv2d_destroy": (None, [_P]),
     "rt_conv2d_out_dims": (None, [_P, C.POINTER(_I), C.POINTER(_I)]),

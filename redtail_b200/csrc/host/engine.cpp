@@ -344,6 +344,11 @@ struct ConvStep {
     rt_conv3d_plan* plan = nullptr;
     int in_id = -1, out_id = -1, skip_id = -1;
     std::string name;
+    // CostVolume -> Conv3D pair replaced by the separable formulation (rt_costvol_conv3d_*): inputs are the two feature maps.
+    bool cvfused = false;
+    rt_costvol_conv3d_desc cvdesc{};
+    rt_cvconv_plan* cvplan = nullptr;
+    int l_id = -1, r_id = -1;
 };
 
 struct PadInfo { int in_id; int planes; int layer; };
@@ -391,6 +396,7 @@ public:
         for (auto* p : configured_plugins_) p->terminate();
         for (auto* p : conv2d_plans_) rt_conv2d_destroy(p);
         for (auto* p : conv3d_plans_) rt_conv3d_destroy(p);
+        for (auto* p : cvconv_plans_) rt_costvol_conv3d_destroy(p);
         if (arena_) cudaFree(arena_);
         if (workspace_) cudaFree(workspace_);
     }
@@ -431,6 +437,7 @@ public:
     std::vector<IPlugin*> configured_plugins_;
     std::vector<rt_conv2d_plan*> conv2d_plans_;
     std::vector<rt_conv3d_plan*> conv3d_plans_;
+    std::vector<rt_cvconv_plan*> cvconv_plans_;
     std::vector<std::unique_ptr<ConvStep>> conv_steps_;
 
 private:
@@ -534,7 +541,7 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                 // A 2-D convolution is a 3-D one with V = D = 1: when the channel counts fit the tensor-core tiles the
                 // tower convs run on the same tcgen05 implicit-GEMM kernel as the 3-D stack ([K,1,H,W] == [K,H,W]).
                 const char* pe2 = getenv("REDTAIL_CONV3D_PRECISION");
-                const bool simt_only = pe2 && !strcmp(pe2, "simt");
+                const bool simt_only = (pe2 && !strcmp(pe2, "simt")) || getenv("REDTAIL_SIMT_TOWERS") != nullptr;
                 if (fusion && !simt_only && d.kind == LKind::kConv && cd.cin % 16 == 0 && cd.cout <= 128) {
                     rt_conv3d_desc c3{};
                     c3.k = cd.cout; c3.v = 1; c3.c = cd.cin; c3.r = cd.r; c3.s = cd.s;
@@ -790,12 +797,57 @@ bool EngineImpl::assignLayoutsAndCreatePlans(bool fusion)
 {
     const int ns = static_cast<int>(steps_.size());
     const int nt = static_cast<int>(slots_.size());
+    // Debug aid: REDTAIL_SIMT_LAYERS="conv3D_2,deconv3D_3" runs the named fused layers on the exact-fp32 CUDA-core kernels
+    // (used to attribute the disparity error to individual layers).
+    if (const char* sl = getenv("REDTAIL_SIMT_LAYERS")) {
+        const std::string list = std::string(",") + sl + ",";
+        for (auto& st : steps_)
+            if (st.conv && list.find("," + st.conv->name + ",") != std::string::npos) st.conv->desc.precision = RT_PREC_SIMT;
+    }
+    // CostVolume(kDefault) whose only consumer is a 3x3x3 / stride-1 / pad-1 Conv3D: the pair collapses into two 2-D
+    // convolutions of the feature maps + one combine pass (costvol_conv3d.cu); the volume is never built.
+    const char* cv_env = getenv("REDTAIL_ENGINE_CVCONV");
+    if (fusion && !(cv_env && cv_env[0] == '0')) {
+        for (int si = 0; si < ns; ++si) {
+            Step& cv = steps_[si];
+            if (cv.costvol_d <= 0 || cv.out.size() != 1 || slots_[cv.out[0]].binding >= 0) continue;
+            const int t = cv.out[0];
+            int user = -1, nusers = 0;
+            for (int sj = 0; sj < ns; ++sj)
+                for (int id : steps_[sj].in)
+                    if (id == t) { user = sj; ++nusers; }
+            if (nusers != 1 || !steps_[user].conv) continue;
+            ConvStep* cs = steps_[user].conv;
+            const rt_conv3d_desc& d = cs->desc;
+            if (cs->in_id != t || cs->skip_id >= 0 || d.transposed || d.pad_end_d != 0) continue;
+            if (d.v != 3 || d.r != 3 || d.s != 3 || d.c != 2 * cv.costvol_c) continue;
+            bool unit = true;
+            for (int i = 0; i < 3; ++i) unit = unit && d.stride[i] == 1 && d.pad[i] == 1;
+            if (!unit || d.in_dims[0] != cv.costvol_d || d.in_dims[2] != cv.costvol_h || d.in_dims[3] != cv.costvol_w) continue;
+            rt_costvol_conv3d_desc f{};
+            f.c = cv.costvol_c; f.h = cv.costvol_h; f.w = cv.costvol_w; f.max_disp = cv.costvol_d; f.k = d.k;
+            f.weights_dtype = d.weights_dtype; f.weights = d.weights; f.bias = d.bias;
+            f.precision = d.precision; f.fuse_elu = d.fuse_elu; f.out_transposed = d.out_transposed;
+            f.out_layout = RT_LAYOUT_DENSE;
+            if (!rt_costvol_conv3d_supported(&f)) continue;
+            cs->cvfused = true; cs->cvdesc = f; cs->l_id = cv.in[0]; cs->r_id = cv.in[1]; cs->in_id = -1;
+            steps_[user].in = cv.in;
+            steps_[user].name = cv.name + " + " + steps_[user].name;
+            cv.dropped = true;
+        }
+    }
     std::vector<int> producer(nt, -1);
     std::vector<std::vector<int>> consumers(nt);
     for (int si = 0; si < ns; ++si) {
+        if (steps_[si].dropped) continue;
         for (int id : steps_[si].out) producer[id] = si;
         for (int id : steps_[si].in) consumers[id].push_back(si);
     }
+    auto cvSplitOk = [&](const ConvStep* cs) {
+        rt_costvol_conv3d_desc f = cs->cvdesc;
+        f.out_layout = RT_LAYOUT_SPLIT16; f.out_transposed = 0;
+        return rt_costvol_conv3d_supported(&f) == 1;
+    };
     auto tcOk = [&](const ConvStep* cs, int in_layout, int out_layout) {
         rt_conv3d_desc d = cs->desc;
         d.in_layout = in_layout; d.out_layout = out_layout;
@@ -808,7 +860,7 @@ bool EngineImpl::assignLayoutsAndCreatePlans(bool fusion)
         for (int t = 0; t < nt; ++t) {
             if (slots_[t].binding >= 0 || slots_[t].alias_of >= 0 || producer[t] < 0) continue;
             const Step& ps = steps_[producer[t]];
-            const bool conv_prod = ps.conv && tcOk(ps.conv, RT_LAYOUT_DENSE, RT_LAYOUT_SPLIT16);
+            const bool conv_prod = ps.conv && (ps.conv->cvfused ? cvSplitOk(ps.conv) : tcOk(ps.conv, RT_LAYOUT_DENSE, RT_LAYOUT_SPLIT16));
             const bool cv_prod = ps.costvol_d > 0 && ps.costvol_c % 8 == 0;
             const bool tr_prod = ps.is_transform;              // decided through its input below
             split[t] = (conv_prod || cv_prod || tr_prod) ? 1 : 0;
@@ -824,7 +876,7 @@ bool EngineImpl::assignLayoutsAndCreatePlans(bool fusion)
                 for (int si : consumers[t]) {
                     const Step& c = steps_[si];
                     if (c.is_transform) { ok = ok && split[c.out[0]]; continue; }
-                    if (!c.conv) { ok = false; continue; }
+                    if (!c.conv || c.conv->cvfused) { ok = false; continue; }   // the fused pair reads dense feature maps
                     if (c.conv->in_id == t) ok = ok && tcOk(c.conv, RT_LAYOUT_SPLIT16, split[c.conv->out_id] ? RT_LAYOUT_SPLIT16 : RT_LAYOUT_DENSE);
                     if (c.conv->skip_id == t) ok = ok && split[c.conv->out_id];   // skip shares the output's layout
                 }
@@ -840,6 +892,22 @@ bool EngineImpl::assignLayoutsAndCreatePlans(bool fusion)
     int nsplit = 0;
     for (int si = 0; si < ns; ++si) {
         Step& st = steps_[si];
+        if (st.dropped) continue;
+        if (st.conv && st.conv->cvfused) {
+            ConvStep* cs = st.conv;
+            const bool sp = split[cs->out_id] != 0;
+            cs->cvdesc.out_layout = sp ? RT_LAYOUT_SPLIT16 : RT_LAYOUT_DENSE;
+            if (sp) cs->cvdesc.out_transposed = 0;
+            nsplit += sp;
+            const int rc = rt_costvol_conv3d_create(&cs->cvdesc, &cs->cvplan);
+            if (rc != RT_OK) return fail(cs->name + ": rt_costvol_conv3d_create failed (" + std::to_string(rc) + ")");
+            cvconv_plans_.push_back(cs->cvplan);
+            st.workspace = rt_costvol_conv3d_workspace_size(cs->cvplan, max_batch_);
+            st.run = [cs](int batch, const std::function<void*(int)>& ptr, void* ws, cudaStream_t s) {
+                return rt_costvol_conv3d_enqueue(cs->cvplan, batch, ptr(cs->l_id), ptr(cs->r_id), ptr(cs->out_id), ws, s);
+            };
+            continue;
+        }
         if (st.is_transform && split[st.in[0]] && split[st.out[0]]) {       // no-op on channels-last data
             slots_[st.out[0]].alias_of = st.in[0];
             st.dropped = true;

@@ -52,6 +52,22 @@ template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return
 
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
 
+// RT_LAYOUT_SPLIT16 element split: x = hi + lo / 2048 (hi = fp16(x), lo = fp16((x - hi) * 2048)), 8 channels = one 16-byte
+// vector per plane.
+__device__ __forceinline__ void split_store8(const float (&v)[8], __half* hi, __half* lo) {
+    __align__(16) __half hv[8];
+    __align__(16) __half lv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float x = fminf(fmaxf(v[k], -65504.f), 65504.f);
+        const __half h = __float2half_rn(x);
+        hv[k] = h;
+        lv[k] = __float2half_rn((x - __half2float(h)) * 2048.f);
+    }
+    *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(hv);
+    *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(lv);
+}
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 }  // namespace rt

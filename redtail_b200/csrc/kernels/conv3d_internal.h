@@ -20,6 +20,8 @@ struct rt_conv3d_plan {
 };
 
 namespace rt {
+// Host weight arrays (RT_F32 | RT_F16) -> fp32.
+void host_to_f32(int dtype, const void* src, int64_t count, std::vector<float>& dst);
 bool tc_shape_supported(const rt_conv3d_desc& d);
 int simt_conv3d_enqueue(const rt_conv3d_plan* p, int n, const float* x, const float* skip, float* y, cudaStream_t s);
 // Returns RT_OK and sets p->tc, or RT_ERR_UNSUPPORTED when the shape is outside what the tensor-core kernels cover

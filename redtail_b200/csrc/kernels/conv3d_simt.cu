@@ -223,6 +223,9 @@ float half_bits_to_float(uint16_t h) {
     return f;
 }
 
+}  // namespace
+
+namespace rt {
 void host_to_f32(int dtype, const void* src, int64_t count, std::vector<float>& dst) {
     dst.resize(count);
     if (dtype == RT_F32) memcpy(dst.data(), src, count * 4);
@@ -231,8 +234,7 @@ void host_to_f32(int dtype, const void* src, int64_t count, std::vector<float>& 
         for (int64_t i = 0; i < count; ++i) dst[i] = half_bits_to_float(h[i]);
     }
 }
-
-}  // namespace
+}  // namespace rt
 
 extern "C" {
 

@@ -85,7 +85,8 @@ struct TcParams {
     int lc, ld, lh, lw;      // log2 of: channels per parity class, merged parities along D, H, W
     int split;               // 1: hi/lo operands (RT_PREC_FP32), 0: hi only
     int stages;
-    int chunk_kb;            // K blocks accumulated in TMEM before the epilogue adds them up in fp32 registers
+    int chunk_kb;            // K blocks (stages) accumulated in TMEM before the epilogue adds them up in fp32 registers
+    int chunk_rows;          // < gr: a chunk is closed after this many filter rows inside a stage (chunk_kb == 1)
     int gr;                  // taps per row group (1..3)
     int mt;                  // M tiles (128 positions each, stacked along H) per job: they share the A halo and the weights
     int a_bytes, b_bytes, b_tx, stage_bytes;   // b_bytes: 1 KB-rounded slot, b_tx: bytes the weight TMA actually delivers
@@ -248,7 +249,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             const uint32_t idesc_half = umma_idesc_f16(kTileM, kCoutPad);
             const uint32_t ring_addr = smem_u32(ring);
             const uint32_t stage_bytes = p.stage_bytes, a_bytes = p.a_bytes;
-            const int kc16 = p.kc >> 4, stages = p.stages, chunk_kb = p.chunk_kb, ncb = p.ncb, gr = p.gr;
+            const int kc16 = p.kc >> 4, stages = p.stages, chunk_kb = p.chunk_kb, chunk_rows = p.chunk_rows, ncb = p.ncb, gr = p.gr;
             const uint32_t grp_a16 = (static_cast<uint32_t>(p.tw) * pitch) >> 4;   // one patch row of A, in 16-byte units
             const uint32_t grp_b16 = static_cast<uint32_t>(p.b_bytes) >> 4;
             const uint32_t tile_a16 = (static_cast<uint32_t>(kTileM) * pitch) >> 4;    // next M tile of the job (th patch rows down)
@@ -259,41 +260,58 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
                 const JobCoord jc = decode_job(p, job);
                 const int nkb = p.cls[jc.cls].ntaps * ncb;
-                for (int kb0 = 0; kb0 < nkb; kb0 += chunk_kb) {
-                    const int kb1 = min(nkb, kb0 + chunk_kb);
-                    mbar_wait(&tmem_empty[buf], bphase ^ 1);                   // epilogue drained this buffer
+                // A chunk (one TMEM accumulation chain) is closed after `chunk_rows` filter rows inside a stage when chains
+                // are shorter than a stage, else after `chunk_kb` whole stages; the epilogue walks the same sequence.
+                bool open = false;
+                int rows_in_chunk = 0, kb_in_chunk = 0;
+                uint32_t d0 = 0;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t d0 = tmem_base + static_cast<uint32_t>(buf * kBufCols);
-                    for (int kb = kb0; kb < kb1; ++kb) {
-                        mbar_wait(&full_bar[stage], phase);
-                        tc_fence_after();
-                        const uint32_t st_addr = ring_addr + static_cast<uint32_t>(stage) * stage_bytes;
-                        uint32_t lo_a = (st_addr >> 4) | (1u << 16);
-                        uint32_t lo_l = ((st_addr + a_bytes) >> 4) | (1u << 16);
-                        uint32_t lo_b = ((st_addr + (SPLIT ? 2u : 1u) * a_bytes) >> 4) | (1u << 16);
-                        const int nr = gr == 1 ? 1 : p.cls[jc.cls].taps[kb / ncb].nr;
+                    const uint32_t st_addr = ring_addr + static_cast<uint32_t>(stage) * stage_bytes;
+                    const uint32_t lo_a = (st_addr >> 4) | (1u << 16);
+                    const uint32_t lo_l = ((st_addr + a_bytes) >> 4) | (1u << 16);
+                    const uint32_t lo_b = ((st_addr + (SPLIT ? 2u : 1u) * a_bytes) >> 4) | (1u << 16);
+                    const int nr = gr == 1 ? 1 : p.cls[jc.cls].taps[kb / ncb].nr;
+                    ++kb_in_chunk;
+                    // The rows of a stage are issued in segments that end where a chunk ends; with chains of a stage or
+                    // longer (chunk_rows == gr) a segment is the whole stage.
+                    for (int i0 = 0; i0 < nr;) {
+                        if (!open) {
+                            mbar_wait(&tmem_empty[buf], bphase ^ 1);           // epilogue drained this buffer
+                            tc_fence_after();
+                            d0 = tmem_base + static_cast<uint32_t>(buf * kBufCols);
+                        }
+                        const int i1 = chunk_rows < gr ? min(nr, i0 + chunk_rows - rows_in_chunk) : nr;
+                        const bool last_seg = i1 == nr;
+                        const bool close = chunk_rows < gr ? true : (kb_in_chunk == chunk_kb || kb == nkb - 1);
                         if (elect_one_sync()) {
-                            for (int i = 0; i < nr; ++i) {                     // taps of the row group share the A box
+                            for (int i = i0; i < i1; ++i) {                    // taps of the row group share the A box
 #pragma unroll
                                 for (int mt = 0; mt < MT; ++mt) {              // M tiles of the job share the weight tile
                                     uint32_t xa = lo_a + i * grp_a16 + mt * tile_a16, xl = lo_l + i * grp_a16 + mt * tile_a16;
                                     uint32_t xb = lo_b + i * grp_b16;
                                     const uint32_t dt = d0 + mt * kAccCols;
                                     for (int kk = 0; kk < kc16; ++kk) {
-                                        umma_f16(dt, desc_hi | xa, desc_hi | xb, idesc_full, (kb > kb0 || i > 0 || kk > 0) ? 1u : 0u);
+                                        umma_f16(dt, desc_hi | xa, desc_hi | xb, idesc_full, (open || i > i0 || kk > 0) ? 1u : 0u);
                                         if (SPLIT) umma_f16(dt + kCoutPad, desc_hi | xl, desc_hi | xb, idesc_half, 1u);
                                         xa += 2; xl += 2; xb += 2;             // +32 bytes = one K=16 slice inside the swizzle atom
                                     }
                                 }
                             }
-                            umma_commit(&empty_bar[stage]);                    // slot free once these MMAs retire
+                            if (last_seg) umma_commit(&empty_bar[stage]);      // slot free once these MMAs retire
+                            if (close) umma_commit(&tmem_full[buf]);           // chunk complete
                         }
                         __syncwarp();
-                        if (++stage == stages) { stage = 0; phase ^= 1; }
+                        rows_in_chunk += i1 - i0;
+                        i0 = i1;
+                        open = !close;
+                        if (close) {
+                            rows_in_chunk = 0; kb_in_chunk = 0;
+                            if (++buf == kNumBuf) { buf = 0; bphase ^= 1; }
+                        }
                     }
-                    if (elect_one_sync()) umma_commit(&tmem_full[buf]);        // chunk complete
-                    __syncwarp();
-                    if (++buf == kNumBuf) { buf = 0; bphase ^= 1; }
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -306,7 +324,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         const int col0 = half * CPH;
         int buf = 0;
         uint32_t bphase = 0;
-        const int chunk_kb = p.chunk_kb;
+        const int chunk_kb = p.chunk_kb, chunk_rows = p.chunk_rows;
         for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
             const JobCoord jc = decode_job(p, job);
             const ClassInfo& ci = p.cls[jc.cls];
@@ -323,23 +341,31 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 }
             }
             for (int kb0 = 0; kb0 < nkb; kb0 += chunk_kb) {
+              // chunks inside this (group of) stage(s): see the MMA issuer
+              const int nsub = chunk_rows < p.gr ? (ci.taps[kb0 / p.ncb].nr + chunk_rows - 1) / chunk_rows : 1;
+              for (int sub = 0; sub < nsub; ++sub) {
                 mbar_wait(&tmem_full[buf], bphase);
                 tc_fence_after();
                 constexpr int LW = CPH >= 16 ? 16 : 8;   // columns per tcgen05.ld
+                constexpr int BW = CPH >= 32 ? 32 : CPH; // columns in flight per wait: all loads of a batch are issued
+                                                         // before the single tcgen05.wait::ld (the drain is latency-bound)
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                           static_cast<uint32_t>(buf * kBufCols + mt * kAccCols + col0);
 #pragma unroll
-                    for (int c0 = 0; c0 < CPH; c0 += LW) {
-                        uint32_t v0[LW], v1[LW];
-                        tmem_ld<LW>(trow + c0, v0);
-                        if (SPLIT) tmem_ld<LW>(trow + kCoutPad + c0, v1);
+                    for (int b0 = 0; b0 < CPH; b0 += BW) {
+                        uint32_t v0[BW], v1[SPLIT ? BW : 1];
+#pragma unroll
+                        for (int c0 = 0; c0 < BW; c0 += LW) {
+                            tmem_ld<LW>(trow + b0 + c0, *reinterpret_cast<uint32_t(*)[LW]>(&v0[c0]));
+                            if (SPLIT) tmem_ld<LW>(trow + kCoutPad + b0 + c0, *reinterpret_cast<uint32_t(*)[LW]>(&v1[c0]));
+                        }
                         tmem_ld_wait();
 #pragma unroll
-                        for (int k = 0; k < LW; ++k) {
-                            acc0[mt][c0 + k] += __uint_as_float(v0[k]);
-                            if (SPLIT) acc1[mt][c0 + k] += __uint_as_float(v1[k]);
+                        for (int k = 0; k < BW; ++k) {
+                            acc0[mt][b0 + k] += __uint_as_float(v0[k]);
+                            if (SPLIT) acc1[mt][b0 + k] += __uint_as_float(v1[k]);
                         }
                     }
                 }
@@ -347,6 +373,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[buf]);
                 if (++buf == kNumBuf) { buf = 0; bphase ^= 1; }
+              }
             }
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
@@ -754,9 +781,16 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     // Chain length (MMA K-steps accumulated inside the tensor core before a round-to-nearest add in registers): 8 for
     // problems big enough to be throughput-bound; 2 when the whole problem is a few waves of tiles, where the extra
     // TMEM round trips are free and the reference's tightest unit-test tolerances (1e-4 on values ~200) need it.
+    const int per_row = p.kc / 16, per_stage = p.gr * per_row;          // MMA K-steps per filter row / per stage
     int chain = p.jobs_per_sample < 4 * 148 ? 2 : 8;
+    // Every chunk costs a TMEM drain (tcgen05.ld moves 64 B/clk/SM and does not overlap the MMAs' own TMEM traffic), so the
+    // big layers close a chunk once per stage (6 K-steps for <= 32 input channels, 12 for 64-channel blocks) rather than
+    // inside it; REDTAIL_TC_CHAIN=<n> forces n K-steps (sub-stage when n is shorter than a stage).
+    if (chain == 8 && per_stage <= 12) chain = per_stage;
     if (const char* e = getenv("REDTAIL_TC_CHAIN")) chain = atoi(e) > 0 ? atoi(e) : chain;
-    p.chunk_kb = split ? (chain / (p.gr * (p.kc / 16)) > 0 ? chain / (p.gr * (p.kc / 16)) : 1) : (1 << 30);
+    if (!split) { p.chunk_kb = 1 << 30; p.chunk_rows = p.gr; }
+    else if (chain >= per_stage) { p.chunk_kb = chain / per_stage; p.chunk_rows = p.gr; }
+    else { p.chunk_kb = 1; p.chunk_rows = chain / per_row > 0 ? chain / per_row : 1; }
     p.stages = (196 * 1024) / p.stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) { cudaFree(t->w_dev); delete t; return RT_ERR_UNSUPPORTED; }

@@ -9,20 +9,6 @@
 namespace rt {
 namespace {
 
-__device__ __forceinline__ void split_store8(const float (&v)[8], __half* hi, __half* lo) {
-    __align__(16) __half hv[8];
-    __align__(16) __half lv[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float x = fminf(fmaxf(v[k], -65504.f), 65504.f);
-        const __half h = __float2half_rn(x);
-        hv[k] = h;
-        lv[k] = __float2half_rn((x - __half2float(h)) * 2048.f);
-    }
-    *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(hv);
-    *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(lv);
-}
-
 // One CTA: 64 consecutive x of one (n, y) row, all 2C channels, all D disparities.
 // The fp32 -> (hi, lo) split and the channel transpose are done ONCE per source element into shared memory, already in
 // the output's 16-byte channel-vector order; the D output runs are then plain LDS.128 -> STG.128 copies (the right half

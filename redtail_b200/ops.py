@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from ._lib import kernels_lib, Conv3dDesc, Conv2dDesc
+from ._lib import kernels_lib, Conv3dDesc, Conv2dDesc, CostvolConv3dDesc
 
 RT_F32, RT_F16 = 0, 1
 PREC_FP32, PREC_FP16, PREC_SIMT = 0, 1, 2
@@ -257,6 +257,60 @@ class Conv3d:
         try:
             if getattr(self, "_plan", None):
                 kernels_lib().rt_conv3d_destroy(self._plan)
+        except Exception:
+            pass
+
+
+class CostVolumeConv3d:
+    """Fused CostVolumePlugin(kDefault) -> Conv3DPlugin(3x3x3, stride 1, pad 1) [-> Transform] [-> ELU].
+
+    left, right [N,C,H,W] fp32 -> [N,K,D,H,W] ([N,D,K,H,W] with out_transposed) fp32, or half [N,2,D,H,W,K] (split16).
+    weights KVCRS [K,3,2C,3,3].  The cost volume is never materialised (include/redtail_b200.h, rt_costvol_conv3d_*).
+    """
+
+    def __init__(self, weights, bias, in_chw, max_disp, precision=PREC_FP32, fuse_elu=False, out_transposed=False,
+                 out_layout=LAYOUT_DENSE):
+        w = np.ascontiguousarray(weights)
+        assert w.ndim == 5 and w.dtype in (np.float32, np.float16)
+        b = None if bias is None else np.ascontiguousarray(bias).astype(w.dtype)
+        c, h, wd = in_chw
+        assert w.shape[1:] == (3, 2 * c, 3, 3), w.shape
+        d = CostvolConv3dDesc()
+        d.c, d.h, d.w, d.max_disp, d.k = c, h, wd, int(max_disp), w.shape[0]
+        d.weights_dtype = RT_F32 if w.dtype == np.float32 else RT_F16
+        d.weights = w.ctypes.data
+        d.bias = b.ctypes.data if b is not None else None
+        d.precision, d.fuse_elu, d.out_transposed, d.out_layout = precision, int(fuse_elu), int(out_transposed), int(out_layout)
+        self.desc = d
+        self._plan = C.c_void_p()
+        rc = kernels_lib().rt_costvol_conv3d_create(C.byref(d), C.byref(self._plan))
+        if rc != 0:
+            raise RedtailError("rt_costvol_conv3d_create failed with status %d" % rc)
+        self._ws = None
+
+    def __call__(self, left, right):
+        _dev(left, right)
+        d = self.desc
+        n = left.shape[0]
+        assert left.dtype == torch.float32 and tuple(left.shape[1:]) == (d.c, d.h, d.w) and right.shape == left.shape
+        if d.out_layout == LAYOUT_SPLIT16:
+            y = torch.empty((n, 2, d.max_disp, d.h, d.w, d.k), dtype=torch.float16, device=left.device)
+        elif d.out_transposed:
+            y = torch.empty((n, d.max_disp, d.k, d.h, d.w), dtype=torch.float32, device=left.device)
+        else:
+            y = torch.empty((n, d.k, d.max_disp, d.h, d.w), dtype=torch.float32, device=left.device)
+        lib = kernels_lib()
+        need = lib.rt_costvol_conv3d_workspace_size(self._plan, n)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=left.device)
+        _check(lib.rt_costvol_conv3d_enqueue(self._plan, n, _p(left), _p(right), _p(y), _p(self._ws), _stream()),
+               "rt_costvol_conv3d_enqueue")
+        return y
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None):
+                kernels_lib().rt_costvol_conv3d_destroy(self._plan)
         except Exception:
             pass
 

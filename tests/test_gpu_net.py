@@ -64,6 +64,19 @@ def test_nvsmall_parity():
     assert err.max() <= TOL_FP32
 
 
+def test_nvsmall_materialised_cost_volume_path():
+    """REDTAIL_ENGINE_CVCONV=0: the 1 GB cost volume is written and conv3D_1 runs as a 3-D convolution (every reference
+    layer executed literally); the default engine uses the separable cost_vol+conv3D_1 step instead.  Same parity bar,
+    and the two engines agree with each other well inside it."""
+    a, e1 = _run("nvsmall", 321, 1025)
+    b, e0 = _run("nvsmall", 321, 1025, REDTAIL_ENGINE_CVCONV="0")
+    assert e0.num_layers == e1.num_layers + 1
+    gold = _golden("nvsmall", 1025, 321)
+    print("separable max %.3g, materialised max %.3g, between %.3g" % (np.abs(a[0] - gold).max(), np.abs(b[0] - gold).max(), np.abs(a - b).max()))
+    assert np.abs(b[0] - gold).max() <= TOL_FP32
+    assert np.abs(a - b).max() <= TOL_FP32
+
+
 def test_nvtiny_unfused_engine_matches_fused():
     """REDTAIL_ENGINE_FUSION=0 executes every plugin through its own enqueue(), as TensorRT would."""
     a, e1 = _run("nvtiny", 161, 513)
@@ -100,7 +113,8 @@ def test_execute_host_roundtrip():
 
 
 @pytest.mark.parametrize("env", [{"REDTAIL_ENGINE_SPLIT16": "0"}, {"REDTAIL_TC_NOGROUP": "1"}, {"REDTAIL_TC_MT1": "1"},
-                                 {"REDTAIL_TC_CHAIN": "2"}])
+                                 {"REDTAIL_TC_CHAIN": "2"}, {"REDTAIL_ENGINE_CVCONV": "0"},
+                                 {"REDTAIL_ENGINE_CVCONV": "0", "REDTAIL_ENGINE_SPLIT16": "0"}])
 def test_nvtiny_engine_variants_agree(env):
     """Engine / kernel variants that are off by default (dense fp32 activations between convs, no row groups, one M tile
     per job, short accumulation chains) all meet the same parity bar."""

@@ -370,3 +370,24 @@ def test_conv3d_transpose_split16_skip(R):
     yin = R.dense_to_split16(y.permute(0, 2, 1, 3, 4).contiguous().cuda())     # [N,D,K,H,W] -> split16 [D][H][W][K]
     out = R.split16_to_dense(op(yin, R.dense_to_split16(skip.cuda())))
     check(out, ref, 3e-4)
+
+
+# ---- fused CostVolume -> Conv3D (the volume is never built): same values as the unfused plugin pair ----
+@pytest.mark.parametrize("prec,tol", [("simt", 2e-4), ("fp32", 2e-4)])
+@pytest.mark.parametrize("n,c,k,h,w_,disp", [(1, 32, 32, 11, 70, 13), (2, 16, 16, 5, 9, 5), (1, 32, 8, 7, 131, 48)])
+def test_costvol_conv3d_fused(R, prec, tol, n, c, k, h, w_, disp):
+    g = torch.Generator().manual_seed(c + k + w_)
+    l, r = torch.randn(n, c, h, w_, generator=g), torch.randn(n, c, h, w_, generator=g)
+    w = torch.randn(k, 3, 2 * c, 3, 3, generator=g) * (1.0 / np.sqrt(27 * 2 * c))
+    b = torch.randn(k, generator=g)
+    cv = O.cost_volume(l, r, disp)                                              # [N,D,2C,H,W]
+    ref = O.elu(O.transform(O.conv3d(cv.double(), w.double(), b.double(), (1, 1, 1), (1, 1, 1)))).float()   # [N,D,K,H,W]
+    p = {"simt": R.PREC_SIMT, "fp32": R.PREC_FP32}[prec]
+    op = R.CostVolumeConv3d(w.numpy(), b.numpy(), (c, h, w_), disp, precision=p, fuse_elu=True, out_transposed=True)
+    check(op(l.cuda(), r.cuda()), ref, tol)
+    assert R.last_kernel() == "cvconv_combine_kernel"
+    op = R.CostVolumeConv3d(w.numpy(), b.numpy(), (c, h, w_), disp, precision=p, fuse_elu=False, out_transposed=False)
+    ref_nt = O.conv3d(cv.double(), w.double(), b.double(), (1, 1, 1), (1, 1, 1)).float()                      # [N,K,D,H,W]
+    check(op(l.cuda(), r.cuda()), ref_nt, tol)
+    op = R.CostVolumeConv3d(w.numpy(), b.numpy(), (c, h, w_), disp, precision=p, fuse_elu=True, out_layout=R.LAYOUT_SPLIT16)
+    check(R.split16_to_dense(op(l.cuda(), r.cuda())), ref, tol + 4 * 2 ** -20)
