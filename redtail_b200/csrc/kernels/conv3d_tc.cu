@@ -65,6 +65,7 @@ struct ClassInfo {
     int dc, hc, wc;          // class-local extent of the GEMM-M lattice
     int tiles_h, tiles_w;
     int job_begin;           // first job index of this class (per sample)
+    unsigned long long nr_pack;   // taps[t].nr, 2 bits per tap (kept in a register by the MMA issuer)
     TapEntry taps[kMaxTaps];
 };
 
@@ -265,14 +266,23 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 bool open = false;
                 int rows_in_chunk = 0, kb_in_chunk = 0;
                 uint32_t d0 = 0;
+                // (no divisions or dependent constant loads between the MMAs of consecutive stages: the tensor pipe idles
+                // whenever this warp is not blocked issuing, so the per-stage scalar path is kept minimal)
+                unsigned long long nrp = p.cls[jc.cls].nr_pack;
+                int cb_left = 0, nr = 1;
                 for (int kb = 0; kb < nkb; ++kb) {
+                    if (cb_left == 0) {                                        // next tap (row group): ncb stages share its nr
+                        nr = gr == 1 ? 1 : static_cast<int>(nrp & 3ull);
+                        nrp >>= 2;
+                        cb_left = ncb;
+                    }
+                    --cb_left;
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t st_addr = ring_addr + static_cast<uint32_t>(stage) * stage_bytes;
                     const uint32_t lo_a = (st_addr >> 4) | (1u << 16);
                     const uint32_t lo_l = ((st_addr + a_bytes) >> 4) | (1u << 16);
                     const uint32_t lo_b = ((st_addr + (SPLIT ? 2u : 1u) * a_bytes) >> 4) | (1u << 16);
-                    const int nr = gr == 1 ? 1 : p.cls[jc.cls].taps[kb / ncb].nr;
                     ++kb_in_chunk;
                     // The rows of a stage are issued in segments that end where a chunk ends; with chains of a stage or
                     // longer (chunk_rows == gr) a segment is the whole stage.
@@ -701,6 +711,11 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
                         }
             }
     p.jobs_per_sample = job;
+    for (int ci = 0; ci < p.nclasses; ++ci) {
+        unsigned long long pack = 0;
+        for (int t2 = 0; t2 < p.cls[ci].ntaps; ++t2) pack |= static_cast<unsigned long long>(p.cls[ci].taps[t2].nr & 3u) << (2 * t2);
+        p.cls[ci].nr_pack = pack;
+    }
 
     // Weight packing: [tile][cb][row][kc] fp16; row = accumulator column (hi), cout_pad + column (lo, fp32 mode).
     const int ntap = static_cast<int>(tiles.size());
@@ -786,7 +801,7 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     // Every chunk costs a TMEM drain (tcgen05.ld moves 64 B/clk/SM and does not overlap the MMAs' own TMEM traffic), so the
     // big layers close a chunk once per stage (6 K-steps for <= 32 input channels, 12 for 64-channel blocks) rather than
     // inside it; REDTAIL_TC_CHAIN=<n> forces n K-steps (sub-stage when n is shorter than a stage).
-    if (chain == 8 && per_stage <= 12) chain = per_stage;
+    if (chain == 8 && per_stage > 8 && per_stage <= 12) chain = per_stage;
     if (const char* e = getenv("REDTAIL_TC_CHAIN")) chain = atoi(e) > 0 ? atoi(e) : chain;
     if (!split) { p.chunk_kb = 1 << 30; p.chunk_rows = p.gr; }
     else if (chain >= per_stage) { p.chunk_kb = chain / per_stage; p.chunk_rows = p.gr; }
