@@ -35,6 +35,12 @@ int rt_stereo_execute_host(rt_stereo_engine* engine, int batch, const float* lef
 /* Runs once with per-layer CUDA-event timing (IProfiler) and writes "layer name\tms\n" lines into buf. */
 int rt_stereo_profile(rt_stereo_engine* engine, int batch, const float* left, const float* right, float* disp,
                       char* buf, size_t buf_len);
+/* Engine plan (ICudaEngine::serialize / IRuntime::deserializeCudaEngine with StereoDnnPluginFactory, the flow of
+ * sample_app/main.cpp:207-220,270-275 -- which the reference could only use for ResNet18_2D because its Conv3D plugins
+ * do not serialise).  rt_stereo_serialize copies the plan into buf when buf_len suffices and always returns the plan
+ * size (0 on error); rt_stereo_deserialize rebuilds an engine from it (no weight file needed). */
+size_t rt_stereo_serialize(const rt_stereo_engine* engine, void* buf, size_t buf_len);
+int rt_stereo_deserialize(const void* plan, size_t plan_size, rt_stereo_engine** engine);
 /* Introspection. */
 int rt_stereo_num_layers(const rt_stereo_engine* engine);
 size_t rt_stereo_device_bytes(const rt_stereo_engine* engine);

@@ -109,7 +109,10 @@ ILayer* addSoftargmax(IPluginContainer& plugin_factory, INetworkDefinition& netw
 class StereoDnnPluginFactory: public IPluginFactory
 {
 public:
-    enum class PluginType { kElu = 0, kCostVolume = 1, kSoftargmax = 2 };
+    /* 0..2 are the reference's tags (lib/internal_utils.h); 3..7 extend the scheme to the plugins the reference could not
+     * serialise (conv3d_plugin.cpp:224-229 asserts), so that NVSmall/NVTiny/ResNet-18 plans can be saved and reloaded too. */
+    enum class PluginType { kElu = 0, kCostVolume = 1, kSoftargmax = 2,
+                            kConv3D = 3, kConv3DTranspose = 4, kTransform = 5, kPadding = 6, kSlice = 7 };
 
     StereoDnnPluginFactory(IPluginContainer& container);
 

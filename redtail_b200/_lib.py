@@ -81,6 +81,8 @@ ENGINE_API = {
     "rt_stereo_enqueue": (_I, [_P, _I, _P, _P, _P, _P]),
     "rt_stereo_execute_host": (_I, [_P, _I, _P, _P, _P]),
     "rt_stereo_profile": (_I, [_P, _I, _P, _P, _P, C.c_char_p, C.c_size_t]),
+    "rt_stereo_serialize": (C.c_size_t, [_P, _P, C.c_size_t]),
+    "rt_stereo_deserialize": (_I, [_P, C.c_size_t, C.POINTER(_P)]),
     "rt_stereo_num_layers": (_I, [_P]),
     "rt_stereo_device_bytes": (C.c_size_t, [_P]),
     "rt_stereo_last_error": (C.c_char_p, []),

@@ -39,6 +39,68 @@ size_t volume(const Dims& d) { return DimsUtils::getTensorSize(d); }
 
 void logMsg(ILogger& log, ILogger::Severity sev, const std::string& s) { log.log(sev, s.c_str()); }
 
+// Little-endian plan (de)serialisation helpers.
+struct PlanWriter {
+    std::string buf;
+    template <typename T> void put(T v) { buf.append(reinterpret_cast<const char*>(&v), sizeof(T)); }
+    void str(const std::string& v) { put<int32_t>(static_cast<int32_t>(v.size())); buf.append(v); }
+    void dims(const Dims& d) { put<int32_t>(d.nbDims); for (int i = 0; i < Dims::MAX_DIMS; ++i) put<int32_t>(d.d[i]); }
+    void align8() { while (buf.size() % 8) buf.push_back('\0'); }
+    void weights(const Weights& w)
+    {
+        put<int32_t>(static_cast<int32_t>(w.type));
+        put<int64_t>(w.values ? w.count : 0);
+        align8();
+        if (w.values && w.count > 0) buf.append(static_cast<const char*>(w.values), w.count * (w.type == DataType::kHALF ? 2 : 4));
+    }
+};
+struct PlanReader {
+    const char* base; size_t size; size_t pos = 0; bool ok = true;
+    template <typename T> T get()
+    {
+        T v{};
+        if (pos + sizeof(T) > size) { ok = false; return v; }
+        memcpy(&v, base + pos, sizeof(T));
+        pos += sizeof(T);
+        return v;
+    }
+    std::string str()
+    {
+        const int32_t n = get<int32_t>();
+        if (!ok || n < 0 || pos + n > size) { ok = false; return std::string(); }
+        std::string v(base + pos, n);
+        pos += n;
+        return v;
+    }
+    Dims dims() { Dims d{}; d.nbDims = get<int32_t>(); for (int i = 0; i < Dims::MAX_DIMS; ++i) d.d[i] = get<int32_t>(); return d; }
+    void align8() { pos = (pos + 7) & ~static_cast<size_t>(7); }
+    Weights weights()          // values point into the plan copy the engine keeps alive
+    {
+        Weights w{DataType::kFLOAT, nullptr, 0};
+        w.type = static_cast<DataType>(get<int32_t>());
+        w.count = get<int64_t>();
+        align8();
+        const size_t bytes = static_cast<size_t>(w.count) * (w.type == DataType::kHALF ? 2 : 4);
+        if (!ok || w.count < 0 || pos + bytes > size) { ok = false; w.count = 0; return w; }
+        w.values = w.count > 0 ? base + pos : nullptr;
+        pos += bytes;
+        return w;
+    }
+};
+constexpr char kPlanMagic[8] = {'R', 'T', 'B', '2', 'P', 'L', 'A', 'N'};
+constexpr int32_t kPlanVersion = 1;
+
+class HostMemoryImpl : public IHostMemory {
+public:
+    explicit HostMemoryImpl(std::string d) : data_(std::move(d)) {}
+    void* data() const override { return const_cast<char*>(data_.data()); }
+    std::size_t size() const override { return data_.size(); }
+    DataType type() const override { return DataType::kINT8; }
+    void destroy() override { delete this; }
+private:
+    std::string data_;
+};
+
 // ------------------------------------------------------------------------------------------------------------------
 // Network definition
 // ------------------------------------------------------------------------------------------------------------------
@@ -414,16 +476,26 @@ public:
     int getMaxBatchSize() const override { return max_batch_; }
     int getNbLayers() const override { return static_cast<int>(steps_.size()); }
     size_t getWorkspaceSize() const override { return workspace_bytes_; }
+    // The plan is the network description (layers, parameters, weights, the plugins' own serialisation blobs) plus the
+    // build settings: building is deterministic and takes milliseconds (no autotuning), so deserialisation replays the
+    // description through the same INetworkDefinition calls and builds again -- plugin layers come back through the
+    // caller's IPluginFactory exactly as in TensorRT (sample_app/main.cpp:207-220).
     IHostMemory* serialize() const override
     {
-        logMsg(log_, ILogger::Severity::kERROR, "ICudaEngine::serialize: engine plans are not serialisable in this build.");
-        return nullptr;
+        if (plan_.empty()) {
+            logMsg(log_, ILogger::Severity::kERROR, "ICudaEngine::serialize: a plugin of this network does not implement serialize().");
+            return nullptr;
+        }
+        return new HostMemoryImpl(plan_);
     }
     IExecutionContext* createExecutionContext() override { return new ContextImpl(this); }
     void destroy() override { delete this; }
 
     bool build(NetworkImpl& net, int max_batch, bool half2);
+    static std::string serializeNetwork(NetworkImpl& net, int max_batch, bool half2);
 
+    std::string plan_;                                  // serialised network (empty if some plugin cannot serialise)
+    std::shared_ptr<std::string> plan_storage_;         // deserialised engines: the blob copy the layer weights point into
     ILogger& log_;
     int max_batch_ = 1;
     int nb_inputs_ = 0;
@@ -785,7 +857,61 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
         steps_.push_back(std::move(st));
     }
     if (!assignLayoutsAndCreatePlans(fusion)) return false;
-    return planMemory();
+    if (!planMemory()) return false;
+    plan_ = serializeNetwork(net, max_batch_, half2);
+    return true;
+}
+
+std::string EngineImpl::serializeNetwork(NetworkImpl& net, int max_batch, bool half2)
+{
+    PlanWriter w;
+    w.buf.append(kPlanMagic, 8);
+    w.put<int32_t>(kPlanVersion);
+    w.put<int32_t>(max_batch);
+    w.put<uint8_t>(half2 ? 1 : 0);
+    w.put<int32_t>(static_cast<int32_t>(net.inputs_.size()));
+    for (auto* t : net.inputs_) { w.put<int32_t>(t->id); w.str(t->name); w.put<int32_t>(static_cast<int32_t>(t->type)); w.dims(t->dims); }
+    w.put<int32_t>(static_cast<int32_t>(net.layers_.size()));
+    for (auto& ln : net.layers_) {
+        const LayerData& d = ln->d;
+        w.put<int32_t>(static_cast<int32_t>(d.kind));
+        w.str(d.name);
+        w.put<int32_t>(static_cast<int32_t>(d.in.size()));
+        for (auto* t : d.in) w.put<int32_t>(t->id);
+        w.put<int32_t>(static_cast<int32_t>(d.out.size()));
+        for (auto* t : d.out) { w.put<int32_t>(t->id); w.str(t->name); }
+        switch (d.kind) {
+            case LKind::kConv:
+            case LKind::kDeconv:
+                w.put<int32_t>(d.nb_out_maps);
+                w.put<int32_t>(d.ksize.h()); w.put<int32_t>(d.ksize.w());
+                w.put<int32_t>(d.stride.h()); w.put<int32_t>(d.stride.w());
+                w.put<int32_t>(d.pad.h()); w.put<int32_t>(d.pad.w());
+                w.weights(d.kw); w.weights(d.bw);
+                break;
+            case LKind::kScale:
+                w.put<int32_t>(static_cast<int32_t>(d.smode));
+                w.weights(d.shift); w.weights(d.scale); w.weights(d.power);
+                break;
+            case LKind::kActivation: w.put<int32_t>(static_cast<int32_t>(d.act)); break;
+            case LKind::kEltwise: w.put<int32_t>(static_cast<int32_t>(d.eop)); break;
+            case LKind::kConcat: break;
+            case LKind::kShuffle: w.put<uint8_t>(d.has_reshape ? 1 : 0); w.dims(d.reshape); break;
+            case LKind::kPlugin: {
+                const size_t n = d.plugin->getSerializationSize();
+                if (n == 0) return std::string();          // a third-party plugin without serialisation: no plan
+                w.put<int64_t>(static_cast<int64_t>(n));
+                w.align8();
+                const size_t at = w.buf.size();
+                w.buf.resize(at + n);
+                d.plugin->serialize(&w.buf[at]);
+                break;
+            }
+        }
+    }
+    w.put<int32_t>(static_cast<int32_t>(net.outputs_.size()));
+    for (auto* t : net.outputs_) w.put<int32_t>(t->id);
+    return w.buf;
 }
 
 // Decides which activation tensors live in RT_LAYOUT_SPLIT16 (channels-last fp16 hi/lo, what the tcgen05 conv kernel
@@ -1105,10 +1231,124 @@ private:
 class RuntimeImpl : public IRuntime {
 public:
     explicit RuntimeImpl(ILogger& log) : log_(log) {}
-    ICudaEngine* deserializeCudaEngine(const void*, size_t, IPluginFactory*) override
+    ICudaEngine* deserializeCudaEngine(const void* blob, size_t size, IPluginFactory* factory) override
     {
-        logMsg(log_, ILogger::Severity::kERROR, "deserializeCudaEngine: engine plans are not serialisable in this build.");
-        return nullptr;
+        auto fail = [&](const std::string& why) -> ICudaEngine* {
+            logMsg(log_, ILogger::Severity::kERROR, "deserializeCudaEngine: " + why);
+            return nullptr;
+        };
+        if (!blob || size < 16 || memcmp(blob, kPlanMagic, 8) != 0) return fail("not a redtail_b200 plan");
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail("no CUDA device (this engine has no CPU path).");
+        // The layer weights of the rebuilt network point into this copy; the engine keeps it alive.
+        auto storage = std::make_shared<std::string>(static_cast<const char*>(blob), size);
+        PlanReader r{storage->data(), storage->size()};
+        r.pos = 8;
+        if (r.get<int32_t>() != kPlanVersion) return fail("unsupported plan version");
+        const int max_batch = r.get<int32_t>();
+        const bool half2 = r.get<uint8_t>() != 0;
+        std::unique_ptr<NetworkImpl> net(new NetworkImpl(log_));
+        std::map<int, ITensor*> tensors;                       // plan tensor id -> tensor of the rebuilt network
+        const int nin = r.get<int32_t>();
+        for (int i = 0; r.ok && i < nin; ++i) {
+            const int id = r.get<int32_t>();
+            const std::string name = r.str();
+            const DataType type = static_cast<DataType>(r.get<int32_t>());
+            const Dims dims = r.dims();
+            tensors[id] = net->addInput(name.c_str(), type, dims);
+        }
+        const int nl = r.get<int32_t>();
+        for (int li = 0; r.ok && li < nl; ++li) {
+            const LKind kind = static_cast<LKind>(r.get<int32_t>());
+            const std::string name = r.str();
+            std::vector<ITensor*> in;
+            const int n_in = r.get<int32_t>();
+            for (int i = 0; i < n_in; ++i) {
+                auto it = tensors.find(r.get<int32_t>());
+                if (it == tensors.end() || it->second == nullptr) return fail(name + ": input tensor not defined yet");
+                in.push_back(it->second);
+            }
+            std::vector<std::pair<int, std::string>> outs;
+            const int n_out = r.get<int32_t>();
+            for (int i = 0; i < n_out; ++i) { const int id = r.get<int32_t>(); outs.emplace_back(id, r.str()); }
+            if (!r.ok || in.empty()) return fail("truncated plan");
+            ILayer* layer = nullptr;
+            switch (kind) {
+                case LKind::kConv:
+                case LKind::kDeconv: {
+                    const int maps = r.get<int32_t>();
+                    const int kh = r.get<int32_t>(), kw_ = r.get<int32_t>();
+                    const int sh = r.get<int32_t>(), sw = r.get<int32_t>();
+                    const int ph = r.get<int32_t>(), pw = r.get<int32_t>();
+                    const Weights kw = r.weights(), bw = r.weights();
+                    if (kind == LKind::kConv) {
+                        auto* l = net->addConvolution(*in[0], maps, DimsHW(kh, kw_), kw, bw);
+                        l->setStride(DimsHW(sh, sw)); l->setPadding(DimsHW(ph, pw));
+                        layer = l;
+                    } else {
+                        auto* l = net->addDeconvolution(*in[0], maps, DimsHW(kh, kw_), kw, bw);
+                        l->setStride(DimsHW(sh, sw)); l->setPadding(DimsHW(ph, pw));
+                        layer = l;
+                    }
+                    break;
+                }
+                case LKind::kScale: {
+                    const ScaleMode mode = static_cast<ScaleMode>(r.get<int32_t>());
+                    const Weights shift = r.weights(), scale = r.weights(), power = r.weights();
+                    layer = net->addScale(*in[0], mode, shift, scale, power);
+                    break;
+                }
+                case LKind::kActivation: layer = net->addActivation(*in[0], static_cast<ActivationType>(r.get<int32_t>())); break;
+                case LKind::kEltwise:
+                    if (in.size() != 2) return fail(name + ": element-wise layer needs two inputs");
+                    layer = net->addElementWise(*in[0], *in[1], static_cast<ElementWiseOperation>(r.get<int32_t>()));
+                    break;
+                case LKind::kConcat: layer = net->addConcatenation(in.data(), static_cast<int>(in.size())); break;
+                case LKind::kShuffle: {
+                    const bool has = r.get<uint8_t>() != 0;
+                    const Dims rd = r.dims();
+                    auto* l = net->addShuffle(*in[0]);
+                    if (has) l->setReshapeDimensions(rd);
+                    layer = l;
+                    break;
+                }
+                case LKind::kPlugin: {
+                    const int64_t n = r.get<int64_t>();
+                    r.align8();
+                    if (!r.ok || n <= 0 || r.pos + static_cast<size_t>(n) > r.size) return fail(name + ": truncated plugin blob");
+                    if (factory == nullptr) return fail(name + ": the plan contains plugin layers but no IPluginFactory was given");
+                    IPlugin* plugin = factory->createPlugin(name.c_str(), r.base + r.pos, static_cast<size_t>(n));
+                    r.pos += static_cast<size_t>(n);
+                    if (plugin == nullptr) return fail(name + ": IPluginFactory::createPlugin returned null");
+                    auto* ext = dynamic_cast<IPluginExt*>(plugin);
+                    layer = ext ? net->addPluginExt(in.data(), static_cast<int>(in.size()), *ext)
+                                : net->addPlugin(in.data(), static_cast<int>(in.size()), *plugin);
+                    break;
+                }
+                default: return fail("unknown layer kind in plan");
+            }
+            if (!r.ok || layer == nullptr) return fail(name + ": truncated plan");
+            layer->setName(name.c_str());
+            if (layer->getNbOutputs() != static_cast<int>(outs.size())) return fail(name + ": output count mismatch");
+            for (size_t i = 0; i < outs.size(); ++i) {
+                layer->getOutput(static_cast<int>(i))->setName(outs[i].second.c_str());
+                tensors[outs[i].first] = layer->getOutput(static_cast<int>(i));
+            }
+        }
+        const int nout = r.get<int32_t>();
+        for (int i = 0; r.ok && i < nout; ++i) {
+            auto it = tensors.find(r.get<int32_t>());
+            if (it == tensors.end()) return fail("output tensor not defined");
+            net->markOutput(*it->second);
+        }
+        if (!r.ok) return fail("truncated plan");
+        auto* e = new EngineImpl(log_);
+        e->plan_storage_ = storage;
+        if (!e->build(*net, max_batch, half2)) {
+            delete e;
+            return nullptr;
+        }
+        return e;
     }
     void destroy() override { delete this; }
 

@@ -261,6 +261,53 @@ int rt_stereo_create(const char* model, int height, int width, int max_disp, con
     return RT_OK;
 }
 
+size_t rt_stereo_serialize(const rt_stereo_engine* e, void* buf, size_t buf_len)
+{
+    if (!e || !e->engine) return 0;
+    IHostMemory* m = e->engine->serialize();
+    if (!m) { g_last_error = "rt_stereo_serialize: " + e->log.last_error; return 0; }
+    const size_t n = m->size();
+    if (buf && buf_len >= n) memcpy(buf, m->data(), n);
+    m->destroy();
+    return n;
+}
+
+int rt_stereo_deserialize(const void* plan, size_t plan_size, rt_stereo_engine** out)
+{
+    if (!plan || plan_size == 0 || !out) { g_last_error = "rt_stereo_deserialize: bad argument"; return RT_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_last_error = "rt_stereo_deserialize: no CUDA device -- this engine has no CPU path";
+        return RT_ERR_NO_DEVICE;
+    }
+    std::unique_ptr<rt_stereo_engine> e(new rt_stereo_engine());
+    e->plugins = IPluginContainer::create(e->log);
+    StereoDnnPluginFactory factory(*e->plugins);
+    IRuntime* runtime = createInferRuntime(e->log);
+    e->engine = runtime->deserializeCudaEngine(plan, plan_size, &factory);
+    runtime->destroy();
+    if (!e->engine) {
+        g_last_error = "rt_stereo_deserialize: " + e->log.last_error;
+        return RT_ERR_UNSUPPORTED;
+    }
+    const int li = e->engine->getBindingIndex("left");
+    if (li < 0 || e->engine->getBindingIndex("right") < 0 || e->engine->getBindingIndex("disp") < 0) {
+        g_last_error = "rt_stereo_deserialize: plan has no left/right/disp bindings";
+        rt_stereo_destroy(e.release());
+        return RT_ERR_ARG;
+    }
+    const Dims d = e->engine->getBindingDimensions(li);
+    e->h = d.d[1]; e->w = d.d[2]; e->max_batch = e->engine->getMaxBatchSize();
+    e->context = e->engine->createExecutionContext();
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_last_error = "cudaStreamCreate failed";
+        rt_stereo_destroy(e.release());
+        return RT_ERR_NO_DEVICE;
+    }
+    *out = e.release();
+    return RT_OK;
+}
+
 void rt_stereo_destroy(rt_stereo_engine* e)
 {
     if (!e) return;

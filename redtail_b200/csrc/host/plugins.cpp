@@ -390,12 +390,45 @@ public:
         if (plan_ == nullptr) return -1;
         return rt_conv3d_enqueue(plan_, batchSize, inputs[0], nullptr, outputs[0], workspace, stream);
     }
-    // Not serialisable in the reference either (conv3d_plugin.cpp:224-229 asserts); the engine serialises these
-    // layers itself from opInfo().
-    size_t getSerializationSize() override { return 0; }
-    void serialize(void*) override {}
+    // The reference asserts here (conv3d_plugin.cpp:224-229: "not implemented"), which is why only ResNet18_2D plans could
+    // be saved.  Blob: tag | kernel dims KVCRS | out dims (transposed) | stride | pad start | pad end | weight type |
+    // kernel count | bias count | kernel bytes | bias bytes; StereoDnnPluginFactory::createPlugin is the reader.
+    size_t getSerializationSize() override { return blob().size(); }
+    void serialize(void* buffer) override { auto b = blob(); memcpy(buffer, b.data(), b.size()); }
+
+    // Deserialised plugins own their weights (the plan blob is only valid during createPlugin()).
+    void ownWeights()
+    {
+        const size_t es = info_.kernel.type == DataType::kHALF ? 2 : 4;
+        owned_kernel_.assign(static_cast<const char*>(info_.kernel.values), static_cast<const char*>(info_.kernel.values) + info_.kernel.count * es);
+        info_.kernel.values = owned_kernel_.data();
+        if (info_.bias.count > 0) {
+            owned_bias_.assign(static_cast<const char*>(info_.bias.values), static_cast<const char*>(info_.bias.values) + info_.bias.count * es);
+            info_.bias.values = owned_bias_.data();
+        }
+    }
 
 private:
+    std::string blob() const
+    {
+        ByteWriter w;
+        w.put<int32_t>(static_cast<int32_t>(transposed_ ? StereoDnnPluginFactory::PluginType::kConv3DTranspose
+                                                         : StereoDnnPluginFactory::PluginType::kConv3D));
+        for (int i = 0; i < 5; i++) w.put<int32_t>(info_.kernel_dims.d[i]);
+        for (int i = 0; i < 4; i++) w.put<int32_t>(transposed_ ? info_.out_dims.d[i] : 0);
+        for (int i = 0; i < 3; i++) w.put<int32_t>(info_.stride.d[i]);
+        for (int i = 0; i < 3; i++) w.put<int32_t>(info_.pad_start.d[i]);
+        for (int i = 0; i < 3; i++) w.put<int32_t>(info_.pad_end.d[i]);
+        w.put<int32_t>(static_cast<int32_t>(info_.kernel.type));
+        w.put<int64_t>(info_.kernel.count);
+        w.put<int64_t>(info_.bias.count);
+        const size_t es = info_.kernel.type == DataType::kHALF ? 2 : 4;
+        w.buf.append(static_cast<const char*>(info_.kernel.values), info_.kernel.count * es);
+        if (info_.bias.count > 0) w.buf.append(static_cast<const char*>(info_.bias.values), info_.bias.count * es);
+        return w.buf;
+    }
+    std::vector<char> owned_kernel_, owned_bias_;
+
     void createPlan()
     {
         rt_conv3d_desc d{};
@@ -469,8 +502,14 @@ public:
         return rt_transpose01(RT_F32, inputs[0], outputs[0], batchSize, in_dims_.d[0], in_dims_.d[1],
                               static_cast<int64_t>(in_dims_.d[2]) * in_dims_.d[3], stream);
     }
-    size_t getSerializationSize() override { return 0; }
-    void serialize(void*) override {}
+    size_t getSerializationSize() override { return 5 * sizeof(int32_t); }
+    void serialize(void* buffer) override
+    {
+        ByteWriter w;
+        w.put<int32_t>(static_cast<int32_t>(StereoDnnPluginFactory::PluginType::kTransform));
+        for (int i = 0; i < 4; i++) w.put<int32_t>(info_.perm.order[i]);
+        memcpy(buffer, w.buf.data(), w.buf.size());
+    }
 
 private:
     OpInfo info_;
@@ -517,8 +556,14 @@ public:
         const int64_t plane = static_cast<int64_t>(in_dims_.d[1]) * in_dims_.d[2] * in_dims_.d[3];
         return rt_pad_planes(RT_F32, inputs[0], outputs[0], batchSize, in_dims_.d[0], plane, info_.pad_end_planes, stream);
     }
-    size_t getSerializationSize() override { return 0; }
-    void serialize(void*) override {}
+    size_t getSerializationSize() override { return 2 * sizeof(int32_t); }
+    void serialize(void* buffer) override
+    {
+        ByteWriter w;
+        w.put<int32_t>(static_cast<int32_t>(StereoDnnPluginFactory::PluginType::kPadding));
+        w.put<int32_t>(info_.pad_end_planes);
+        memcpy(buffer, w.buf.data(), w.buf.size());
+    }
 
 private:
     OpInfo info_;
@@ -566,8 +611,16 @@ public:
         return rt_slice_planes(RT_F32, inputs[0], outputs[0], batchSize, in_dims_.d[0], plane,
                                info_.slice_start, info_.slice_end, stream);
     }
-    size_t getSerializationSize() override { return 0; }
-    void serialize(void*) override {}
+    size_t getSerializationSize() override { return 7 * sizeof(int32_t); }
+    void serialize(void* buffer) override
+    {
+        ByteWriter w;
+        w.put<int32_t>(static_cast<int32_t>(StereoDnnPluginFactory::PluginType::kSlice));
+        for (int i = 0; i < 4; i++) w.put<int32_t>(in_dims_.d[i]);
+        w.put<int32_t>(info_.slice_start);
+        w.put<int32_t>(info_.slice_end);
+        memcpy(buffer, w.buf.data(), w.buf.size());
+    }
 
 private:
     OpInfo info_;
@@ -736,6 +789,50 @@ IPlugin* StereoDnnPluginFactory::createPlugin(const char* layerName, const void*
         case PluginType::kElu:        return container_.deserializeEluPlugin(layerName, rest, rest_len);
         case PluginType::kCostVolume: return container_.deserializeCostVolumePlugin(layerName, rest, rest_len);
         case PluginType::kSoftargmax: return container_.deserializeSoftargmaxPlugin(layerName, rest, rest_len);
+        case PluginType::kConv3D:
+        case PluginType::kConv3DTranspose: {
+            ByteReader r{rest, rest_len};
+            const bool tr = static_cast<PluginType>(tag) == PluginType::kConv3DTranspose;
+            Dims kd{}; kd.nbDims = 5;
+            for (int i = 0; i < 5; i++) kd.d[i] = r.get<int32_t>();
+            int od[4];
+            for (int i = 0; i < 4; i++) od[i] = r.get<int32_t>();
+            int st[3], ps[3], pe[3];
+            for (int i = 0; i < 3; i++) st[i] = r.get<int32_t>();
+            for (int i = 0; i < 3; i++) ps[i] = r.get<int32_t>();
+            for (int i = 0; i < 3; i++) pe[i] = r.get<int32_t>();
+            const DataType wt = static_cast<DataType>(r.get<int32_t>());
+            const int64_t kcount = r.get<int64_t>(), bcount = r.get<int64_t>();
+            const size_t es = wt == DataType::kHALF ? 2 : 4;
+            assert(kcount > 0 && bcount >= 0 && r.left == static_cast<size_t>(kcount + bcount) * es);
+            Weights kw{wt, r.p, kcount};
+            Weights bw{wt, bcount > 0 ? r.p + kcount * es : nullptr, bcount};
+            IPlugin* p = tr ? container_.createConv3DTransposePlugin(Conv3DType::kTensorFlow, kd, DimsNCHW(od[0], od[1], od[2], od[3]),
+                                                                     DimsCHW(st[0], st[1], st[2]), DimsCHW(ps[0], ps[1], ps[2]),
+                                                                     DimsCHW(pe[0], pe[1], pe[2]), kw, bw, layerName)
+                            : container_.createConv3DPlugin(Conv3DType::kTensorFlow, kd, DimsCHW(st[0], st[1], st[2]),
+                                                            DimsCHW(ps[0], ps[1], ps[2]), DimsCHW(pe[0], pe[1], pe[2]), kw, bw, layerName);
+            if (auto* c = dynamic_cast<Conv3DPluginBase*>(p)) c->ownWeights();   // serialData is only valid during this call
+            return p;
+        }
+        case PluginType::kTransform: {
+            ByteReader r{rest, rest_len};
+            Permutation perm{};
+            for (int i = 0; i < 4; i++) perm.order[i] = r.get<int32_t>();
+            return container_.createTransformPlugin(perm, layerName);
+        }
+        case PluginType::kPadding: {
+            ByteReader r{rest, rest_len};
+            return container_.createPaddingPlugin(DimsNCHW(0, 0, 0, 0), DimsNCHW(r.get<int32_t>(), 0, 0, 0), layerName);
+        }
+        case PluginType::kSlice: {
+            ByteReader r{rest, rest_len};
+            int d[4];
+            for (int i = 0; i < 4; i++) d[i] = r.get<int32_t>();
+            const int s0 = r.get<int32_t>(), s1 = r.get<int32_t>();
+            return container_.createSlicePlugin(DimsNCHW(d[0], d[1], d[2], d[3]), DimsNCHW(s0, 0, 0, 0),
+                                                DimsNCHW(s1, d[1], d[2], d[3]), layerName);
+        }
     }
     assert(false);
     return nullptr;

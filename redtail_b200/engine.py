@@ -27,12 +27,35 @@ class StereoEngine:
         if rc != 0:
             raise RedtailError("rt_stereo_create failed (%d): %s" % (rc, self.lib.rt_stereo_last_error().decode()))
 
+    def serialize(self):
+        """-> bytes: the engine plan (ICudaEngine::serialize)."""
+        n = self.lib.rt_stereo_serialize(self._e, None, 0)
+        if n == 0:
+            raise RedtailError("rt_stereo_serialize failed: %s" % self.lib.rt_stereo_last_error().decode())
+        buf = C.create_string_buffer(n)
+        self.lib.rt_stereo_serialize(self._e, buf, n)
+        return buf.raw
+
+    @classmethod
+    def deserialize(cls, plan):
+        """Engine from a plan (IRuntime::deserializeCudaEngine + StereoDnnPluginFactory); no weight file needed."""
+        if not torch.cuda.is_available():
+            raise RedtailError("StereoEngine needs a CUDA device (there is no CPU path)")
+        self = cls.__new__(cls)
+        self.lib = engine_lib()
+        self._e = C.c_void_p()
+        rc = self.lib.rt_stereo_deserialize(plan, len(plan), C.byref(self._e))
+        if rc != 0:
+            raise RedtailError("rt_stereo_deserialize failed (%d): %s" % (rc, self.lib.rt_stereo_last_error().decode()))
+        self.h = self.w = self.max_batch = None      # taken from the plan by the library
+        return self
+
     def __call__(self, left, right, out=None):
         """Device tensors in, device tensor out; asynchronous on the current torch stream."""
         assert left.is_cuda and right.is_cuda and left.dtype == torch.float32 and left.is_contiguous() and right.is_contiguous()
         n = left.shape[0]
         if out is None:
-            out = torch.empty((n, self.h, self.w), dtype=torch.float32, device=left.device)
+            out = torch.empty((n, left.shape[2], left.shape[3]), dtype=torch.float32, device=left.device)
         rc = self.lib.rt_stereo_enqueue(self._e, n, C.c_void_p(left.data_ptr()), C.c_void_p(right.data_ptr()),
                                         C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         if rc != 0:
@@ -51,7 +74,7 @@ class StereoEngine:
     def profile(self, left, right):
         """-> list of (layer name, ms), measured with CUDA events around every engine step."""
         n = left.shape[0]
-        out = torch.empty((n, self.h, self.w), dtype=torch.float32, device=left.device)
+        out = torch.empty((n, left.shape[2], left.shape[3]), dtype=torch.float32, device=left.device)
         buf = C.create_string_buffer(1 << 16)
         torch.cuda.synchronize()
         rc = self.lib.rt_stereo_profile(self._e, n, C.c_void_p(left.data_ptr()), C.c_void_p(right.data_ptr()),

@@ -60,3 +60,26 @@ def test_reference_generated_builder(tmp_path, net, h, w):
     disp = np.fromfile(out, dtype=np.float32).reshape(h, w)
     gold = np.load(os.path.join(oio.GOLDEN, "disp_%s_%dx%d_f64oracle.npy" % (net, w, h)))
     assert np.abs(disp - gold).max() <= 1e-3
+
+
+def test_reference_builder_plan_roundtrip(tmp_path):
+    """sample_app/main.cpp:207-220,270-275: engine->serialize(), then IRuntime::deserializeCudaEngine with
+    StereoDnnPluginFactory after the builder's weights, plugin container and engine are gone.  The reference can do this
+    for ResNet18_2D only (its Conv3D plugins assert in serialize()); here the NVTiny plan round-trips bit-exactly."""
+    exe = _need("nvstereo_net_driver")
+    h, w = 161, 513
+    l, r = oio.load_sample_pair()
+    l, r = oio.resize_pair(l, r, h, w)
+    l.tofile(tmp_path / "l.bin")
+    r.tofile(tmp_path / "r.bin")
+    outs = []
+    for mode in ([], ["plan"]):
+        out = tmp_path / ("disp%d.bin" % len(outs))
+        p = subprocess.run([exe, "nvtiny", str(w), str(h), oio.weights_path("nvtiny"), str(tmp_path / "l.bin"),
+                            str(tmp_path / "r.bin"), str(out)] + mode, capture_output=True, text=True, timeout=600)
+        print(p.stdout[-1000:], p.stderr[-1000:])
+        assert p.returncode == 0
+        if mode:
+            assert "engine rebuilt from it" in p.stdout
+        outs.append(np.fromfile(out, dtype=np.float32))
+    assert np.array_equal(outs[0], outs[1])

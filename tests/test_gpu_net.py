@@ -77,6 +77,31 @@ def test_nvsmall_materialised_cost_volume_path():
     assert np.abs(a - b).max() <= TOL_FP32
 
 
+def test_plan_serialize_deserialize_roundtrip():
+    """ICudaEngine::serialize -> IRuntime::deserializeCudaEngine (+ StereoDnnPluginFactory) through the C-ABI: the plan
+    carries every layer incl. the Conv3D / Conv3DTranspose plugins and their weights; the rebuilt engine needs no weight
+    file and gives bit-identical disparities.  Corrupt plans fail loudly."""
+    from redtail_b200 import StereoEngine
+    from redtail_b200.ops import RedtailError
+    d0, eng = _run("nvtiny", 161, 513)
+    plan = eng.serialize()
+    nlayers = eng.num_layers
+    eng.close()
+    wbytes = os.path.getsize(oio.weights_path("nvtiny"))
+    assert wbytes <= len(plan) <= wbytes + (1 << 20), (len(plan), wbytes)
+    eng2 = StereoEngine.deserialize(plan)
+    assert eng2.num_layers == nlayers
+    l, r = _pair(161, 513)
+    d1 = eng2(torch.from_numpy(l[None]).cuda(), torch.from_numpy(r[None]).cuda()).cpu().numpy()
+    assert np.array_equal(d0, d1)
+    plan2 = eng2.serialize()                           # tensor ids are renumbered in replay order: same size, then a fixed point
+    assert len(plan2) == len(plan)
+    assert StereoEngine.deserialize(plan2).serialize() == plan2
+    for bad in (plan[: len(plan) // 2], b"garbage" * 100, plan[:8] + b"\xff" * 64):
+        with pytest.raises(RedtailError):
+            StereoEngine.deserialize(bad)
+
+
 def test_nvtiny_unfused_engine_matches_fused():
     """REDTAIL_ENGINE_FUSION=0 executes every plugin through its own enqueue(), as TensorRT would."""
     a, e1 = _run("nvtiny", 161, 513)

@@ -3,7 +3,9 @@
 // sample_app/main.cpp:176-315 minus OpenCV (raw CHW float32 .bin images in, raw float32 disparity out).
 // Test infrastructure (tools/dropin); built only where /root/reference exists.
 //
-//   nvstereo_net_driver <nvsmall|nvtiny|resnet18|resnet18_2D> <width> <height> <weights.bin> <left.bin> <right.bin> <out.bin> [profile]
+//   nvstereo_net_driver <nvsmall|nvtiny|resnet18|resnet18_2D> <width> <height> <weights.bin> <left.bin> <right.bin> <out.bin> [profile|plan]
+//   plan: the engine is serialised, destroyed together with the weights and the plugin container, and re-created with
+//         IRuntime::deserializeCudaEngine + StereoDnnPluginFactory (sample_app/main.cpp:207-220,270-275) before it runs.
 #include <NvInfer.h>
 #include <cuda_runtime_api.h>
 
@@ -12,6 +14,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -83,6 +86,24 @@ int main(int argc, char** argv)
     net->destroy();
     builder->destroy();
     if (!engine) { fprintf(stderr, "engine build failed\n"); return 3; }
+    const bool plan_mode = argc > 8 && !strcmp(argv[8], "plan");
+    std::unique_ptr<IPluginContainer> container2;
+    if (plan_mode) {
+        IHostMemory* plan = engine->serialize();
+        if (!plan) { fprintf(stderr, "serialize failed\n"); return 5; }
+        std::string blob(static_cast<const char*>(plan->data()), plan->size());
+        plan->destroy();
+        engine->destroy();
+        container.reset();                                   // nothing of the build survives but the blob
+        keep.clear(); keep.shrink_to_fit(); weights.clear();
+        container2 = IPluginContainer::create(log);
+        StereoDnnPluginFactory factory(*container2);
+        IRuntime* runtime = createInferRuntime(log);
+        engine = runtime->deserializeCudaEngine(blob.data(), blob.size(), &factory);
+        runtime->destroy();
+        if (!engine) { fprintf(stderr, "deserializeCudaEngine failed\n"); return 5; }
+        printf("Plan: %zu bytes, engine rebuilt from it\n", blob.size());
+    }
     if (engine->getNbBindings() != 3) { fprintf(stderr, "expected 3 bindings\n"); return 3; }
     void* buf[3];
     const int il = engine->getBindingIndex("left"), ir = engine->getBindingIndex("right"), io = engine->getBindingIndex("disp");
@@ -92,13 +113,13 @@ int main(int argc, char** argv)
     cudaMemcpy(buf[ir], right.data(), right.size() * 4, cudaMemcpyHostToDevice);
     IExecutionContext* ctx = engine->createExecutionContext();
     Prof prof;
-    if (argc > 8) ctx->setProfiler(&prof);
+    if (argc > 8 && !plan_mode) ctx->setProfiler(&prof);
     const auto t0 = std::chrono::high_resolution_clock::now();
     const bool ok = ctx->execute(1, buf);
     const auto t1 = std::chrono::high_resolution_clock::now();
     if (!ok) { fprintf(stderr, "execute failed\n"); return 4; }
     printf("Host time: %.3f ms (%d engine steps)\n", std::chrono::duration<float, std::milli>(t1 - t0).count(), engine->getNbLayers());
-    if (argc > 8) printf("All layers: %.3f ms\n", prof.total);
+    if (argc > 8 && !plan_mode) printf("All layers: %.3f ms\n", prof.total);
     cudaMemcpy(out.data(), buf[io], out.size() * 4, cudaMemcpyDeviceToHost);
     std::ofstream(argv[7], std::ios::binary).write(reinterpret_cast<const char*>(out.data()), out.size() * 4);
     ctx->destroy();
