@@ -625,7 +625,8 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                     c3.weights_dtype = cd.weights_dtype; c3.weights = cd.weights; c3.bias = cd.bias;
                     c3.precision = pe2 && !strcmp(pe2, "fp16") ? RT_PREC_FP16 : RT_PREC_FP32;
                     c3.fuse_elu = cd.fuse_elu;
-                    if (rt_conv3d_tc_supported(&c3) == 1) {
+                    const char* tw_env = getenv("REDTAIL_ENGINE_TOWER_SPLIT16");
+                    if (tw_env && tw_env[0] == '1' && rt_conv3d_tc_supported(&c3) == 1) {
                         // Deferred like the 3-D layers: the layout pass may keep the activations between consecutive tower
                         // convolutions in RT_LAYOUT_SPLIT16 (no re-layout pass in front of the next conv).
                         conv_steps_.emplace_back(new ConvStep());
@@ -635,6 +636,17 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                         st.conv = cs;
                         st.run = [cs](int batch, const std::function<void*(int)>& ptr, void* ws, cudaStream_t s) {
                             return rt_conv3d_enqueue(cs->plan, batch, ptr(cs->in_id), nullptr, ptr(cs->out_id), ws, s);
+                        };
+                        break;
+                    }
+                    rt_conv3d_plan* p3 = nullptr;
+                    if (rt_conv3d_create(&c3, &p3) == RT_OK) {
+                        conv3d_plans_.push_back(p3);
+                        st.workspace = rt_conv3d_workspace_size(p3, max_batch_);
+                        const int in_id = d.in[0]->id, out_id = out->id;
+                        st.out.push_back(out_id);
+                        st.run = [p3, in_id, out_id](int batch, const std::function<void*(int)>& ptr, void* ws, cudaStream_t s) {
+                            return rt_conv3d_enqueue(p3, batch, ptr(in_id), nullptr, ptr(out_id), ws, s);
                         };
                         break;
                     }
