@@ -626,7 +626,7 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                     c3.precision = pe2 && !strcmp(pe2, "fp16") ? RT_PREC_FP16 : RT_PREC_FP32;
                     c3.fuse_elu = cd.fuse_elu;
                     const char* tw_env = getenv("REDTAIL_ENGINE_TOWER_SPLIT16");
-                    if (tw_env && tw_env[0] == '1' && rt_conv3d_tc_supported(&c3) == 1) {
+                    if (!(tw_env && tw_env[0] == '0') && rt_conv3d_tc_supported(&c3) == 1) {
                         // Deferred like the 3-D layers: the layout pass may keep the activations between consecutive tower
                         // convolutions in RT_LAYOUT_SPLIT16 (no re-layout pass in front of the next conv).
                         conv_steps_.emplace_back(new ConvStep());

@@ -138,7 +138,7 @@ def test_execute_host_roundtrip():
 
 
 @pytest.mark.parametrize("env", [{"REDTAIL_ENGINE_SPLIT16": "0"}, {"REDTAIL_TC_NOGROUP": "1"}, {"REDTAIL_TC_MT1": "1"},
-                                 {"REDTAIL_TC_CHAIN": "2"}, {"REDTAIL_ENGINE_CVCONV": "0"},
+                                 {"REDTAIL_TC_CHAIN": "2"}, {"REDTAIL_ENGINE_CVCONV": "0"}, {"REDTAIL_ENGINE_TOWER_SPLIT16": "0"},
                                  {"REDTAIL_ENGINE_CVCONV": "0", "REDTAIL_ENGINE_SPLIT16": "0"}])
 def test_nvtiny_engine_variants_agree(env):
     """Engine / kernel variants that are off by default (dense fp32 activations between convs, no row groups, one M tile
