@@ -364,8 +364,10 @@ def main():
     literal = None
     if cv_fused and world == 1:
         os.environ["REDTAIL_ENGINE_CVCONV"] = "0"
+        os.environ["REDTAIL_TC_CHAIN"] = "4"       # the setting with which the literal path meets the 1e-3 px bar (tests/test_gpu_net.py)
         eng2 = StereoEngine("nvsmall", H, W, WEIGHTS, max_batch=B)
         del os.environ["REDTAIL_ENGINE_CVCONV"]
+        del os.environ["REDTAIL_TC_CHAIN"]
         for _ in range(3):
             eng2(d_left, d_right, out=d_disp)
         torch.cuda.synchronize()
@@ -377,7 +379,7 @@ def main():
         torch.cuda.synchronize()
         lms = l0.elapsed_time(l1) / args.steps
         literal = {"value": B / (lms * 1e-3), "unit": "stereo pairs/s", "ms_per_step": lms,
-                   "what": "REDTAIL_ENGINE_CVCONV=0: 1.0 GB cost volume written, conv3D_1 as a 438 GFLOP tcgen05 3-D convolution"}
+                   "what": "REDTAIL_ENGINE_CVCONV=0 REDTAIL_TC_CHAIN=4: 1.0 GB cost volume written, conv3D_1 as a 438 GFLOP tcgen05 3-D convolution, 4-K-step accumulation chains (parity-valid setting of that path)"}
         del eng2
 
     pairs = world * B * args.steps

@@ -91,6 +91,9 @@ struct TcParams {
     int gr;                  // taps per row group (1..3)
     int mt;                  // M tiles (128 positions each, stacked along H) per job: they share the A halo and the weights
     int a_bytes, b_bytes, b_tx, stage_bytes;   // b_bytes: 1 KB-rounded slot, b_tx: bytes the weight TMA actually delivers
+    int a_tx;                // bytes one A box delivers (a_bytes is its 1 KB-rounded slot)
+    int hs2;                 // 1: stride-2 conv with a row group: the A box holds EVERY input row ((th-1)*2 + 3 rows of tw = 8
+                             // positions), filter row i starts at box row i and consecutive 8-row groups are 2 box rows apart
     int out_d, out_h, out_w; // output extent actually written
     long long out_sn, out_sc, out_sd;   // element strides of sample, channel, depth in the dense fp32 output
     int fuse_elu;
@@ -222,7 +225,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     for (int cb = 0; cb < p.ncb; ++cb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* st = ring + static_cast<size_t>(stage) * p.stage_bytes;
-                        mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes * (SPLIT ? 2 : 1) + te.nr * p.b_tx);
+                        mbar_arrive_expect_tx(&full_bar[stage], p.a_tx * (SPLIT ? 2 : 1) + te.nr * p.b_tx);
                         tma_load_5d(st, &map_a_hi, &full_bar[stage], cb * p.kc, cw, chh, cd, jc.n);
                         if (SPLIT) tma_load_5d(st + p.a_bytes, &map_a_lo, &full_bar[stage], cb * p.kc, cw, chh, cd, jc.n);
                         for (int i = 0; i < te.nr; ++i)
@@ -245,7 +248,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             const uint32_t pitch = p.kc * 2;                                   // bytes per operand row = swizzle span
             const uint32_t swz = p.kc == 64 ? 2u : (p.kc == 32 ? 4u : 6u);     // SWIZZLE_128B / 64B / 32B
             // descriptor high word: SBO (8 rows) | version 1 (bit 46) | swizzle (bits 61-63); low word: start>>4 | LBO=1
-            const uint64_t desc_hi = (static_cast<uint64_t>(((8u * pitch) >> 4) | (1u << 14) | (swz << 29))) << 32;
+            const uint64_t desc_b_hi = (static_cast<uint64_t>(((8u * pitch) >> 4) | (1u << 14) | (swz << 29))) << 32;
+            // A in hs2 mode: the next 8-row group (= next patch row, tw = 8) is two box rows further
+            const uint64_t desc_hi = (static_cast<uint64_t>((((p.hs2 ? 16u : 8u) * pitch) >> 4) | (1u << 14) | (swz << 29))) << 32;
             const uint32_t idesc_full = umma_idesc_f16(kTileM, kAccCols);
             const uint32_t idesc_half = umma_idesc_f16(kTileM, kCoutPad);
             const uint32_t ring_addr = smem_u32(ring);
@@ -303,8 +308,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                                     uint32_t xb = lo_b + i * grp_b16;
                                     const uint32_t dt = d0 + mt * kAccCols;
                                     for (int kk = 0; kk < kc16; ++kk) {
-                                        umma_f16(dt, desc_hi | xa, desc_hi | xb, idesc_full, (open || i > i0 || kk > 0) ? 1u : 0u);
-                                        if (SPLIT) umma_f16(dt + kCoutPad, desc_hi | xl, desc_hi | xb, idesc_half, 1u);
+                                        umma_f16(dt, desc_hi | xa, desc_b_hi | xb, idesc_full, (open || i > i0 || kk > 0) ? 1u : 0u);
+                                        if (SPLIT) umma_f16(dt + kCoutPad, desc_hi | xl, desc_b_hi | xb, idesc_half, 1u);
                                         xa += 2; xl += 2; xb += 2;             // +32 bytes = one K=16 slice inside the swizzle atom
                                     }
                                 }
@@ -627,8 +632,19 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
         return v2 > 0 ? v2 : 0;
     };
     const int cls_h = lattice(1, 0), cls_w = lattice(2, 0);
+    // Stride-2 forward convs (conv3D_3ds / 6ds): with 8-wide patches one 8-row UMMA group is exactly one patch row, so an A
+    // box that holds every input row lets the three filter rows share it (row i starts at box row i, groups are two box
+    // rows apart) -- 9 stages per tile instead of 27.
+    p.hs2 = 0;
+    if (!tr && d.stride[1] == 2 && d.r == 3 && !getenv("REDTAIL_TC_NOGROUP") && !getenv("REDTAIL_TC_NOHS2")) {
+        const int rows = (16 - 1) * 2 + 3;
+        const int a_g = (rows * 8 * p.kc * 2 + 1023) & ~1023;
+        const int b_g = (nb * p.kc * 2 + 1023) & ~1023;
+        if ((196 * 1024) / (a_g * (split ? 2 : 1) + 3 * b_g) >= 2) p.hs2 = 1;
+    }
     long long best = -1;
-    for (int tw = 8; tw <= 128; tw *= 2) {
+    if (p.hs2) { p.tw = 8; p.th = 16; best = 0; }
+    for (int tw = 8; tw <= 128 && !p.hs2; tw *= 2) {
         const int th = kTileM / tw;
         if (!tr && (tw * d.stride[2] > 256 || th * d.stride[1] > 256)) continue;       // TMA box limit
         const long long area = static_cast<long long>((cls_w + tw - 1) / tw) * tw * ((cls_h + th - 1) / th) * th;
@@ -644,8 +660,8 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     std::vector<Tile> tiles;
     // Row groups (see TapEntry): the H shifts of a class are consecutive (3 filter rows of a stride-1 conv, 2 shifts of
     // a merged-parity transposed conv); they share one A box when >= 2 pipeline stages still fit.  Needs in_s == 1.
-    p.gr = 1;
-    if (p.in_s[0] == 1 && p.in_s[1] == 1 && p.in_s[2] == 1 && !getenv("REDTAIL_TC_NOGROUP")) {
+    p.gr = p.hs2 ? 3 : 1;
+    if (!p.hs2 && p.in_s[0] == 1 && p.in_s[1] == 1 && p.in_s[2] == 1 && !getenv("REDTAIL_TC_NOGROUP")) {
         int want = 1;
         if (!tr) want = d.r;
         else
@@ -670,7 +686,7 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     // Two H-stacked M tiles per job (forward convs with a row group, narrow N): the second tile reuses the weight tiles
     // and shares the 2 halo rows of the A box -- 25 % less L2 -> SM traffic on the L2-bound 32-channel layers.
     p.mt = 1;
-    if (p.gr >= 2 && cout_pad <= 32 && cls_h >= 2 * p.th && !getenv("REDTAIL_TC_MT1")) {
+    if (!p.hs2 && p.gr >= 2 && cout_pad <= 32 && cls_h >= 2 * p.th && !getenv("REDTAIL_TC_MT1")) {
         const int a_g = (2 * p.th + p.gr - 1) * p.tw * p.kc * 2;
         const int b_g = (nb * p.kc * 2 + 1023) & ~1023;
         if ((196 * 1024) / (a_g * (split ? 2 : 1) + p.gr * b_g) >= 2) p.mt = 2;
@@ -787,7 +803,8 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
         if (rc != 0) { cudaFree(t->w_dev); delete t; return rc > 0 ? rc : RT_ERR_UNSUPPORTED; }
     }
     // Shared-memory budget.
-    p.a_bytes = (p.th * p.mt + p.gr - 1) * p.tw * p.kc * 2;
+    p.a_tx = (p.hs2 ? (p.th - 1) * 2 + p.gr : p.th * p.mt + p.gr - 1) * p.tw * p.kc * 2;
+    p.a_bytes = (p.a_tx + 1023) & ~1023;
     p.b_tx = nb * p.kc * 2;
     p.b_bytes = (p.b_tx + 1023) & ~1023;
     p.stage_bytes = p.a_bytes * (split ? 2 : 1) + p.gr * p.b_bytes;
@@ -862,8 +879,8 @@ int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const f
                                 static_cast<uint64_t>(t->cin) * 2 * t->in_w * t->in_h,
                                 static_cast<uint64_t>(t->in_elems) * 4};          // sample stride: hi + lo planes
         const uint32_t box[5] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.tw * p.in_s[2]),
-                                 static_cast<uint32_t>((p.th * p.mt + p.gr - 1) * p.in_s[1]), 1u, 1u};
-        const uint32_t es[5] = {1u, static_cast<uint32_t>(p.in_s[2]), static_cast<uint32_t>(p.in_s[1]), 1u, 1u};
+                                 static_cast<uint32_t>(p.hs2 ? (p.th - 1) * 2 + p.gr : (p.th * p.mt + p.gr - 1) * p.in_s[1]), 1u, 1u};
+        const uint32_t es[5] = {1u, static_cast<uint32_t>(p.in_s[2]), static_cast<uint32_t>(p.hs2 ? 1 : p.in_s[1]), 1u, 1u};
         const CUtensorMapSwizzle swz = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
         int rc = make_tensor_map(&ma_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, hi, dims, st, box, es, swz);
         if (rc == 0 && p.split) rc = make_tensor_map(&ma_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, lo, dims, st, box, es, swz);

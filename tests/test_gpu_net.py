@@ -69,7 +69,9 @@ def test_nvsmall_materialised_cost_volume_path():
     layer executed literally); the default engine uses the separable cost_vol+conv3D_1 step instead.  Same parity bar,
     and the two engines agree with each other well inside it."""
     a, e1 = _run("nvsmall", 321, 1025)
-    b, e0 = _run("nvsmall", 321, 1025, REDTAIL_ENGINE_CVCONV="0")
+    # The literal path adds conv3D_1's 108-K-step sums to the error budget: it meets the bar with 4-K-step accumulation
+    # chains (REDTAIL_TC_CHAIN=4, ~20 % slower); with the default one-chain-per-stage setting it sits right at 1e-3.
+    b, e0 = _run("nvsmall", 321, 1025, REDTAIL_ENGINE_CVCONV="0", REDTAIL_TC_CHAIN="4")
     assert e0.num_layers == e1.num_layers + 1
     gold = _golden("nvsmall", 1025, 321)
     print("separable max %.3g, materialised max %.3g, between %.3g" % (np.abs(a[0] - gold).max(), np.abs(b[0] - gold).max(), np.abs(a - b).max()))
