@@ -10,12 +10,13 @@
 // time.  Activations are first re-laid out channels-last as fp16 ([N][D][H][W][C], see pack kernel) so that the A
 // operand of a tap is a plain TMA box [tw x th x KC] at a shifted coordinate -- zero padding (D, H and W) is TMA
 // out-of-bounds fill, never materialised; stride-2 convolutions use TMA traversal strides.  A transposed convolution
-// of stride s is computed as a sub-pixel convolution: its s^3 output parities ride along GEMM-N (merged while N <= 128,
+// of stride s is computed as a sub-pixel convolution: its s^3 output parities ride along GEMM-N (merged while N <= 64,
 // the rest are separate classes), A tiles are loaded once per SHIFT instead of once per tap, and the epilogue does the
 // depth-to-space scatter.
 //
 // L2 -> SM traffic (what bounds the 32-channel layers) is cut three ways: (1) row groups -- the 3 filter rows of a
-// stride-1 conv read one TMA box that is 2 patch rows taller, at 1 KB-aligned row offsets; (2) two H-stacked M tiles per
+// stride-1 conv read one TMA box that is 2 patch rows taller, at swizzle-period-aligned row offsets (stride-2 convs: 8-wide
+// patches and a box with every input row, see hs2); (2) two H-stacked M tiles per
 // job share those halo rows and the weight tiles; (3) activations between two convolutions stay in RT_LAYOUT_SPLIT16
 // (channels-last fp16 hi/lo planes written by the epilogue), so no re-layout / Transform / Padding pass ever runs.
 //
@@ -27,8 +28,9 @@
 // RT_PREC_FP16 issues only the hi*hi product (the reference's fp16 configs, 1e-2 tolerance).
 //
 // The tensor core accumulates in fp32 with TRUNCATION (measured: a 108-step chain drifts NVSmall's disparity by 6e-3 px),
-// so TMEM chains are kept to ~8-12 K-steps ("chunk") and the epilogue warps add every chunk into fp32 registers with
-// round-to-nearest while the next chunk runs in another TMEM buffer.
+// so TMEM chains are kept to one pipeline stage (6-12 K-steps, a "chunk"; shorter, closed inside a stage, on request) and
+// the epilogue warps add every chunk into fp32 registers with round-to-nearest while the next chunk runs in another TMEM
+// buffer.  What a chunk boundary costs and what it does not (TMEM reads are free) is measured in profiles/r01_ncu_full_kernels.md.
 //
 // CTA = 10 warps: warp 0 TMA producer, warp 1 MMA issuer (elect.sync; + TMEM allocation, all 512 columns = 2..8
 // accumulator buffers), warps 2-9 epilogue (tcgen05.ld -> registers -> bias / skip / ELU -> dense fp32 or split16 stores;
