@@ -1372,6 +1372,21 @@ private:
 
 }  // namespace
 
+// Host-only extension (no CUDA device needed): the plan of a network WITHOUT building it -- the layer list, parameters,
+// weights and plugin blobs exactly as ICudaEngine::serialize() would write them.  Used by tools/dropin (net_driver dump
+// mode) to capture the graphs of the reference's generated builders for the test suite's graph-level checker.
+// Returns the plan size (0 if a plugin cannot serialise); copies it when buf_len suffices.
+extern "C" size_t redtail_serialize_network(void* network, int max_batch, int half2, void* buf, size_t buf_len)
+{
+    if (!network) return 0;
+    NetworkImpl& net = *static_cast<NetworkImpl*>(static_cast<INetworkDefinition*>(network));
+    net.invalidate();
+    if (!net.resolve()) return 0;
+    const std::string plan = EngineImpl::serializeNetwork(net, max_batch > 0 ? max_batch : 1, half2 != 0);
+    if (buf && buf_len >= plan.size()) memcpy(buf, plan.data(), plan.size());
+    return plan.size();
+}
+
 extern "C" void* createInferBuilder_INTERNAL(void* logger, int)
 {
     return static_cast<IBuilder*>(new BuilderImpl(*static_cast<ILogger*>(logger)));

@@ -15,7 +15,8 @@ committed outputs.  What it writes (all under tests/golden/):
   images/kitti_{left,right}_1025x321.f16.npy
                             the sample stereo pair of stereoDNN/sample_app/data
                             (img_{left,right}.bin, CHW float32 in [0,1]) stored as fp16.
-  disp_*.npy                network-level golden disparities computed by the fixture-pinned
+  disp_*.npy                network-level golden disparities (NVSmall, NVTiny: oracle/nets.py; ResNet-18 nets: the reference's
+                            generated builders dumped as plans and executed by oracle/plan.py) computed by the fixture-pinned
                             CPU oracle (oracle/nets.py, float64) on that pair.
 
 Usage: python tests/golden/make_golden.py [--skip-disp]
@@ -54,7 +55,7 @@ def main():
     print("plugin_fixtures.npz:", len(fx), "tensors")
 
     os.makedirs(os.path.join(HERE, "weights"), exist_ok=True)
-    for net, d in (("nvsmall", "NVSmall"), ("nvtiny", "NVTiny")):
+    for net, d in (("nvsmall", "NVSmall"), ("nvtiny", "NVTiny"), ("resnet18", "ResNet-18"), ("resnet18_2D", "ResNet-18_2D")):
         shutil.copyfile(os.path.join(REF, "models", d, "TensorRT", "trt_weights.bin"),
                         os.path.join(HERE, "weights", net + "_fp32.bin"))
         os.chmod(os.path.join(HERE, "weights", net + "_fp32.bin"), 0o644)
@@ -75,6 +76,25 @@ def main():
         wts = oio.read_weights(os.path.join(HERE, "weights", net + "_fp32.bin"))
         l, r = oio.resize_pair(left, right, h, w)
         disp = nets.stereo_forward(net, wts, l, r, dtype=torch.float64)
+        np.save(os.path.join(HERE, "disp_%s_%dx%d_f64oracle.npy" % (net, w, h)), disp.astype(np.float32))
+        print(net, disp.shape, float(disp.min()), float(disp.max()))
+    # ResNet-18 (3-D, 1025x321) and ResNet18_2D (513x257): the reference's own generated builders
+    # (sample_app/resnet18_*_net.cpp, 1036 / 777 lines) are the wiring.  tools/dropin/build.sh compiles them unchanged against
+    # include/NvInfer.h; the net driver's host-only `dump` mode writes the network plan (no GPU), and oracle/plan.py executes
+    # that plan with the fixture-pinned ops in float64.
+    import subprocess
+    from oracle import plan as oplan
+    driver = os.path.join(os.path.dirname(os.path.dirname(HERE)), "dropin", "_ref", "nvstereo_net_driver")
+    for net, (h, w) in (("resnet18_2D", (257, 513)), ("resnet18", (321, 1025))):
+        tmp = "/tmp/make_golden_%s" % net
+        np.zeros(3 * h * w, dtype=np.float32).tofile(tmp + ".z")
+        subprocess.run([driver, net, str(w), str(h), os.path.join(HERE, "weights", net + "_fp32.bin"), tmp + ".z", tmp + ".z",
+                        tmp + ".plan", "dump"], check=True)
+        with open(tmp + ".plan", "rb") as f:
+            pl = oplan.parse(f.read())
+        l, r = oio.resize_pair(left, right, h, w)
+        out = oplan.execute(pl, {"left": l[None].astype(np.float64), "right": r[None].astype(np.float64)})
+        disp = list(out.values())[0].reshape(h, w)
         np.save(os.path.join(HERE, "disp_%s_%dx%d_f64oracle.npy" % (net, w, h)), disp.astype(np.float32))
         print(net, disp.shape, float(disp.min()), float(disp.max()))
 

@@ -45,8 +45,10 @@ def test_reference_gtest_costvolume_perf_shape(tmp_path):
     assert r.returncode == 0
 
 
-@pytest.mark.parametrize("net,h,w", [("nvtiny", 161, 513), ("nvsmall", 321, 1025)])
-def test_reference_generated_builder(tmp_path, net, h, w):
+# px_scale: ResNet18_2D emits sigmoid-normalised disparity; sample_app/main.cpp:325-327 multiplies it by the width.
+@pytest.mark.parametrize("net,h,w,px_scale", [("nvtiny", 161, 513, 1), ("nvsmall", 321, 1025, 1),
+                                              ("resnet18", 321, 1025, 1), ("resnet18_2D", 257, 513, 513)])
+def test_reference_generated_builder(tmp_path, net, h, w, px_scale):
     exe = _need("nvstereo_net_driver")
     l, r = oio.load_sample_pair()
     l, r = oio.resize_pair(l, r, h, w)
@@ -59,7 +61,9 @@ def test_reference_generated_builder(tmp_path, net, h, w):
     assert p.returncode == 0
     disp = np.fromfile(out, dtype=np.float32).reshape(h, w)
     gold = np.load(os.path.join(oio.GOLDEN, "disp_%s_%dx%d_f64oracle.npy" % (net, w, h)))
-    assert np.abs(disp - gold).max() <= 1e-3
+    err = np.abs(disp - gold) * px_scale
+    print("%s: max %.3g px, mean %.3g px" % (net, err.max(), err.mean()))
+    assert err.max() <= 1e-3
 
 
 def test_reference_builder_plan_roundtrip(tmp_path):

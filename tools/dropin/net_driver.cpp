@@ -3,7 +3,7 @@
 // sample_app/main.cpp:176-315 minus OpenCV (raw CHW float32 .bin images in, raw float32 disparity out).
 // Test infrastructure (tools/dropin); built only where /root/reference exists.
 //
-//   nvstereo_net_driver <nvsmall|nvtiny|resnet18|resnet18_2D> <width> <height> <weights.bin> <left.bin> <right.bin> <out.bin> [profile|plan]
+//   nvstereo_net_driver <nvsmall|nvtiny|resnet18|resnet18_2D> <width> <height> <weights.bin> <left.bin> <right.bin> <out.bin> [profile|plan|dump]
 //   plan: the engine is serialised, destroyed together with the weights and the plugin container, and re-created with
 //         IRuntime::deserializeCudaEngine + StereoDnnPluginFactory (sample_app/main.cpp:207-220,270-275) before it runs.
 #include <NvInfer.h>
@@ -24,6 +24,8 @@
 
 using namespace nvinfer1;
 using namespace redtail::tensorrt;
+
+extern "C" size_t redtail_serialize_network(void* network, int max_batch, int half2, void* buf, size_t buf_len);
 
 struct Log : public ILogger {
     void log(Severity s, const char* msg) override { if (s <= Severity::kWARNING) std::cerr << "TRT: " << msg << std::endl; }
@@ -80,6 +82,16 @@ int main(int argc, char** argv)
     else if (model == "resnet18") net = createResNet18_1025x321Network(*builder, *container, DimsCHW{3, h, w}, weights, DataType::kFLOAT, log);
     else if (model == "resnet18_2D") net = createResNet18_2D_513x257Network(*builder, *container, DimsCHW{3, h, w}, weights, DataType::kFLOAT, log);
     else { fprintf(stderr, "unknown model\n"); return 1; }
+    if (argc > 8 && !strcmp(argv[8], "dump")) {
+        // Host-only: write the plan of the network the reference's builder just described (no engine, no GPU) to <out.bin>.
+        const size_t n = redtail_serialize_network(net, 1, 0, nullptr, 0);
+        if (n == 0) { fprintf(stderr, "network is not serialisable\n"); return 5; }
+        std::string blob(n, '\0');
+        redtail_serialize_network(net, 1, 0, &blob[0], n);
+        std::ofstream(argv[7], std::ios::binary).write(blob.data(), blob.size());
+        printf("Network plan: %zu bytes, %d layers\n", n, net->getNbLayers());
+        return 0;
+    }
     builder->setMaxBatchSize(1);
     builder->setMaxWorkspaceSize(size_t(1) << 30);
     ICudaEngine* engine = builder->buildCudaEngine(*net);
