@@ -894,10 +894,12 @@ int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const f
     if (grid > p.njobs) grid = p.njobs;
 #define RT_LAUNCH_UMMA(CPH, SPL, MTT)                                                                                    \
     do {                                                                                                              \
-        static bool attr_set = false;                                                                                 \
-        if (!attr_set) {                                                                                              \
+        static bool attr_set[64] = {};            /* per device: the attribute belongs to the device's copy of the kernel */ \
+        int dev_ = 0;                                                                                                 \
+        RT_CUDA(cudaGetDevice(&dev_));                                                                                \
+        if (dev_ < 0 || dev_ >= 64 || !attr_set[dev_]) {                                                              \
             RT_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<CPH, SPL, MTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-            attr_set = true;                                                                                          \
+            if (dev_ >= 0 && dev_ < 64) attr_set[dev_] = true;                                                        \
         }                                                                                                             \
         conv3d_umma_kernel<CPH, SPL, MTT><<<grid, kThreads, t->smem_bytes, s>>>(ma_hi, ma_lo, t->map_w, p, plan->bias, t->d_cols, skip, y); \
     } while (0)

@@ -257,10 +257,10 @@ int rt_corr_cost_volume(int dtype, const void* left, const void* right, void* ou
     dim3 grid(static_cast<unsigned>(ceil_div(w, 128)), h, n);
     cudaStream_t s = as_stream(stream);
     if (dtype == RT_F32) {
-        if (smem > 48 * 1024) RT_CUDA(cudaFuncSetAttribute(corr_cost_volume_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        if (smem > 48 * 1024) RT_CUDA(cudaFuncSetAttribute(corr_cost_volume_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         corr_cost_volume_kernel<float, 0><<<grid, 128, smem, s>>>(static_cast<const float*>(left), static_cast<const float*>(right), static_cast<float*>(out), c, h, w, max_disp);
     } else if (dtype == RT_F16) {
-        if (smem > 48 * 1024) RT_CUDA(cudaFuncSetAttribute(corr_cost_volume_kernel<__half, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        if (smem > 48 * 1024) RT_CUDA(cudaFuncSetAttribute(corr_cost_volume_kernel<__half, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         corr_cost_volume_kernel<__half, 0><<<grid, 128, smem, s>>>(static_cast<const __half*>(left), static_cast<const __half*>(right), static_cast<__half*>(out), c, h, w, max_disp);
     } else {
         return RT_ERR_UNSUPPORTED;

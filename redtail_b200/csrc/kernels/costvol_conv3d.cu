@@ -296,10 +296,12 @@ int rt_costvol_conv3d_create(const rt_costvol_conv3d_desc* d, rt_cvconv_plan** o
     if (rc == RT_OK) rc = static_cast<int>(cudaMalloc(&p->w_edge, we.size() * sizeof(float)));
     if (rc == RT_OK) rc = static_cast<int>(cudaMemcpy(p->w_edge, we.data(), we.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (rc == RT_OK) {
-        const int smem = static_cast<int>(combine_smem(*d));
+        // The limit is per kernel, not per plan: always raise it to the bound rt_costvol_conv3d_supported() checks against, so a
+        // later plan with a smaller footprint cannot lower it under an earlier plan's needs.
+        const int smem = 200 * 1024;
         cudaError_t e1 = cudaFuncSetAttribute(cvconv_combine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaError_t e2 = cudaFuncSetAttribute(cvconv_combine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaError_t e3 = cudaFuncSetAttribute(cvconv_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(edge_smem(*d)));
+        cudaError_t e3 = cudaFuncSetAttribute(cvconv_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) rc = static_cast<int>(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3);
     }
     if (rc != RT_OK) {

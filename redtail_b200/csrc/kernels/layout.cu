@@ -150,7 +150,7 @@ int rt_cost_volume_split16(const void* left, const void* right, void* out, int n
     if (c % 8 != 0) return RT_ERR_UNSUPPORTED;
     const size_t smem = static_cast<size_t>(c / 8) * (64 + 64 + max_disp - 1) * 2 * sizeof(uint4);
     if (smem > 200 * 1024) return RT_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024) RT_CUDA(cudaFuncSetAttribute(cost_volume_split16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    if (smem > 48 * 1024) RT_CUDA(cudaFuncSetAttribute(cost_volume_split16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     dim3 grid((w + 63) / 64, h, n);
     cost_volume_split16_kernel<<<grid, 256, smem, as_stream(stream)>>>(static_cast<const float*>(left), static_cast<const float*>(right),
                                                                       static_cast<__half*>(out), c, h, w, max_disp);
@@ -164,7 +164,7 @@ int rt_dense_to_split16(const void* x, void* y, int n, int d, int c, int h, int 
     if (c % 8 != 0 || c > 512 || static_cast<long long>(n) * d > 65535 || h > 65535) return RT_ERR_UNSUPPORTED;
     if (n == 0) return RT_OK;
     const size_t smem = static_cast<size_t>(c) * 65 * sizeof(float);
-    if (smem > 48 * 1024) RT_CUDA(cudaFuncSetAttribute(dense_to_split16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    if (smem > 48 * 1024) RT_CUDA(cudaFuncSetAttribute(dense_to_split16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     dim3 grid((w + 63) / 64, h, n * d);
     dense_to_split16_kernel<<<grid, 256, smem, as_stream(stream)>>>(static_cast<const float*>(x), static_cast<__half*>(y), d, c, h, w);
     note_launch("dense_to_split16");
@@ -177,7 +177,7 @@ int rt_split16_to_dense(const void* x, void* y, int n, int d, int c, int h, int 
     if (c > 512 || static_cast<long long>(n) * d > 65535 || h > 65535) return RT_ERR_UNSUPPORTED;
     if (n == 0) return RT_OK;
     const size_t smem = static_cast<size_t>(c) * 65 * sizeof(float);
-    if (smem > 48 * 1024) RT_CUDA(cudaFuncSetAttribute(split16_to_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    if (smem > 48 * 1024) RT_CUDA(cudaFuncSetAttribute(split16_to_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     dim3 grid((w + 63) / 64, h, n * d);
     split16_to_dense_kernel<<<grid, 256, smem, as_stream(stream)>>>(static_cast<const __half*>(x), static_cast<float*>(y), d, c, h, w);
     note_launch("split16_to_dense");
