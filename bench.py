@@ -39,9 +39,10 @@ def synthetic_pairs(batch, seed=1234):
         img = np.zeros((3, H, W), np.float32)
         for c in range(3):
             acc = np.zeros((H, W), np.float32)
-            for _ in range(6):
+            for _ in range(6):               # same draw order as oracle/io.py synthetic_pair (the tests' generator)
                 fx, fy = rng.uniform(0.01, 0.35, 2)
-                acc += rng.uniform(0.3, 1.0) * np.sin(fx * xx + fy * yy + rng.uniform(0, 2 * np.pi))
+                ph = rng.uniform(0, 2 * np.pi)
+                acc += rng.uniform(0.3, 1.0) * np.sin(fx * xx + fy * yy + ph)
             img[c] = (acc - acc.min()) / (acc.max() - acc.min() + 1e-6)
         left = np.clip(img + 0.05 * rng.uniform(0, 1, img.shape).astype(np.float32), 0, 1).astype(np.float32)
         disp = np.where(yy > H * 0.55, 2.0 + 78.0 * (yy - H * 0.55) / (H * 0.45), 2.0 + 20.0 * xx / W)
@@ -175,7 +176,9 @@ def run_reference_arm(args):
     wts = oio.read_weights(WEIGHTS)
     l, r = synthetic_pairs(1)
     cores, t_band = _calibrate_cpu_threads(nets, wts, l, r)
-    budget = 150.0 / max(1, args.steps + args.warmup)
+    # Every step is one FULL 1025x321 pair (same config as the GPU arm).  Only if K+W full passes could not finish in
+    # ~8 minutes on this host is the band cut (and the line then says so in cpu_baseline.sample).
+    budget = 480.0 / max(1, args.steps + args.warmup)
     rows = 321 if t_band * 321 / 33 <= budget else max(33, int(321 * budget / (t_band * 321 / 33)) // 32 * 32 + 1)
     for _ in range(args.warmup):
         nets.stereo_forward("nvsmall", wts, l[0][:, :rows], r[0][:, :rows])
@@ -221,13 +224,15 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- this engine has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION/INFO; stdout must carry exactly one JSON line.
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its debug log to STDOUT unless told otherwise, and stdout must carry exactly one JSON line: send the
+        # INFO log (communicator size, rings/NVLS, transports) to stderr instead of silencing it.
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH,ENV")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from redtail_b200 import StereoEngine, ops
-    from redtail_b200.parallel import gather_disparities
+    from redtail_b200.parallel import OverlappedGather, gather_disparities
     B = args.batch
     eng = StereoEngine("nvsmall", H, W, WEIGHTS, max_batch=B)
     left_np, right_np = synthetic_pairs(B, seed=1234 + 100 * rank)
@@ -237,11 +242,16 @@ def main():
     d_left, d_right = h_left.cuda(), h_right.cuda()
     d_disp = torch.empty((B, H, W), dtype=torch.float32, device="cuda")
     gathered = torch.empty((world * B, H, W), dtype=torch.float32, device="cuda") if world > 1 else None
+    # The one exchange of the path: every rank's disparity maps are collected with an NCCL all-gather over NVLink, issued
+    # on a side stream so that the next step's kernels do not wait for the slowest rank of this one (parallel.py).
+    og = OverlappedGather((B, H, W), torch.float32, torch.device("cuda", local)) if world > 1 else None
 
     def step_device():
-        eng(d_left, d_right, out=d_disp)
-        if world > 1:      # the one exchange of the path: collect every rank's disparity maps (NCCL over NVLink)
-            gather_disparities(d_disp, out=gathered)
+        if og is None:
+            eng(d_left, d_right, out=d_disp)
+        else:
+            eng(d_left, d_right, out=og.next_buffer())
+            og.submit()
 
     def barrier():
         if world > 1:
@@ -259,6 +269,8 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step_device()
+    if og is not None:
+        og.flush()                     # the timed region ends when the LAST step's gather has landed
     e1.record()
     barrier()
     launches = ops.launch_count() - launches0
@@ -293,6 +305,19 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- disparity L1 of the timed workload (BASELINE.json's metric names it): the bench's own synthetic pair (seed 1234,
+    # rank 0) against the float64 oracle's disparity for that pair (tests/golden/make_golden_synth.py; the same check as
+    # tests/test_gpu_net.py::test_nvsmall_synthetic_pairs_parity) ----
+    disparity_l1 = None
+    gpath = os.path.join(ROOT, "tests", "golden", "disp_nvsmall_synth1234_f64oracle.npy")
+    if os.path.exists(gpath):
+        eng(d_left, d_right, out=d_disp)
+        torch.cuda.synchronize()
+        err = np.abs(d_disp[0].cpu().numpy().astype(np.float64) - np.load(gpath).astype(np.float64))
+        disparity_l1 = {"max": float(err.max()), "mean": float(err.mean()), "unit": "px", "tolerance": 1e-3,
+                        "pass": bool(err.max() <= 1e-3),
+                        "vs": "float64 CPU oracle (fixture-pinned ops, reference's weights) on the timed synthetic pair, seed 1234"}
+
     # ---- per-kernel roofline numbers: CUDA events around every engine step, on the engine's stream ----
     peaks = measured_peaks()
     prof_runs = 5
@@ -315,12 +340,16 @@ def main():
                           (" (conv3D_1's 438.4 GFLOP are not executed: cost_vol+conv3D_1 run in the separable form, see roofline_cost_volume_engine)" if cv_fused else ""),
                 "peak_source": peaks["source"] + " cuBLAS bf16 (sustained)", "share_of_step": conv_ms / total_ms if total_ms else None,
                 "precision": os.environ.get("REDTAIL_CONV3D_PRECISION", "fp32") + " (" + ops.last_kernel() + ")"}
-    # DRAM traffic of the dominant kernels from the committed `ncu --set full` capture (profiles/r01_traffic.json).
+    # DRAM traffic cannot be counted from inside an un-profiled run: the figure is the dram__bytes_read+write sum of the
+    # committed ncu capture of this same command (profiles/, newest round), and the line says so; null when there is none.
     traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f)
+    for tname in ("r02_traffic.json", "r01_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f)
+            roofline["traffic_source"] = "ncu capture committed as profiles/" + tname + " (not measured in this run)"
+            break
     roofline["traffic"] = traffic.get("conv3d_stack_bytes_per_pair")
     # Cost volume, as the engine runs it (written straight into the split16 layout conv3D_1 consumes) ...
     if cv_fused:
@@ -397,6 +426,7 @@ def main():
         "e2e": {"value": pairs / e2e_s, "unit": "stereo pairs/s", "h2d_bytes_per_step": int(2 * B * 3 * H * W * 4),
                 "d2h_bytes_per_step": int(B * H * W * 4)},
         "gpu_launches": int(launches),
+        "disparity_l1": disparity_l1,
         "clocks": sampler.summary(),
         "roofline": roofline,
         "roofline_cost_volume": roofline_cv,

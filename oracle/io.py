@@ -46,6 +46,19 @@ def read_weights(path, dtype=np.float32):
     return out
 
 
+def write_fp16_weights(src_fp32, dst):
+    """The reference's fp16 weight file of a net: same entries, payloads rounded to fp16 (the reference's generator writes
+    both files from the same arrays, scripts/tensorrt_model_builder.py:52-60; byte identity with
+    models/*/TensorRT/trt_weights_fp16.bin is checked by tests/golden/make_golden_fp16.py and pinned by fp16_md5.json)."""
+    w = read_weights(src_fp32)
+    with open(dst, "wb") as f:
+        for name, a in w.items():
+            f.write(name.encode() + b"\0")
+            f.write(struct.pack("<I", a.size))
+            f.write(a.astype("<f2").tobytes())
+    return dst
+
+
 def weights_path(net, dtype="fp32"):
     return os.path.join(GOLDEN, "weights", "%s_%s.bin" % (net, dtype))
 

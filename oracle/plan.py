@@ -27,9 +27,15 @@ K_CONV, K_DECONV, K_SCALE, K_ELTWISE, K_CONCAT, K_ACTIVATION, K_SHUFFLE, K_PLUGI
 P_ELU, P_COSTVOL, P_SOFTARGMAX, P_CONV3D, P_CONV3D_T, P_TRANSFORM, P_PADDING, P_SLICE = range(8)
 
 
+def _f16(a):
+    """Values rounded to fp16 (what the reference's trt_weights_fp16.bin holds: it is the elementwise fp16 rounding of
+    trt_weights.bin, checked byte for byte by tests/golden/make_golden_fp16.py)."""
+    return a.astype(np.float16).astype(np.float64)
+
+
 class _Reader:
-    def __init__(self, buf, pos=0):
-        self.b, self.p = buf, pos
+    def __init__(self, buf, pos=0, round_fp16=False):
+        self.b, self.p, self.round_fp16 = buf, pos, round_fp16
 
     def get(self, fmt):
         v = struct.unpack_from("<" + fmt, self.b, self.p)
@@ -56,13 +62,14 @@ class _Reader:
         dt = np.float16 if typ == 1 else np.float32
         a = np.frombuffer(self.b, dtype=dt, count=count, offset=self.p).astype(np.float64) if count else None
         self.p += count * np.dtype(dt).itemsize
-        return a
+        return _f16(a) if (self.round_fp16 and a is not None) else a
 
 
-def parse(buf):
-    """-> dict(max_batch, inputs=[(id, name, dims)], layers=[dict], outputs=[id])."""
+def parse(buf, round_fp16=False):
+    """-> dict(max_batch, inputs=[(id, name, dims)], layers=[dict], outputs=[id]).
+    round_fp16: every weight is rounded to fp16 first -- the network the reference builds from trt_weights_fp16.bin."""
     assert buf[:8] == MAGIC, "not an engine plan"
-    r = _Reader(buf, 8)
+    r = _Reader(buf, 8, round_fp16)
     version, max_batch, _half2 = r.get("i"), r.get("i"), r.get("B")
     assert version == 1
     inputs = []
@@ -93,7 +100,7 @@ def parse(buf):
         elif k == K_PLUGIN:
             n = r.get("q")
             r.align8()
-            L["plugin"] = _parse_plugin(buf[r.p:r.p + n])
+            L["plugin"] = _parse_plugin(buf[r.p:r.p + n], round_fp16)
             r.p += n
         else:
             assert k == K_CONCAT, k
@@ -103,7 +110,7 @@ def parse(buf):
     return {"max_batch": max_batch, "inputs": inputs, "layers": layers, "outputs": outputs}
 
 
-def _parse_plugin(blob):
+def _parse_plugin(blob, round_fp16=False):
     r = _Reader(blob)
     tag = r.get("i")
     P = {"tag": tag}
@@ -124,6 +131,9 @@ def _parse_plugin(blob):
         P["w"] = np.frombuffer(blob, dtype=dt, count=kc, offset=r.p).astype(np.float64).reshape(P["kdims"])
         r.p += kc * np.dtype(dt).itemsize
         P["b"] = np.frombuffer(blob, dtype=dt, count=bc, offset=r.p).astype(np.float64) if bc else None
+        if round_fp16:
+            P["w"] = _f16(P["w"])
+            P["b"] = _f16(P["b"]) if P["b"] is not None else None
     elif tag == P_TRANSFORM:
         P["order"] = r.get("4i")
     elif tag == P_PADDING:

@@ -431,8 +431,13 @@ class EngineImpl;
 
 class ContextImpl : public IExecutionContext {
 public:
-    explicit ContextImpl(EngineImpl* e) : engine_(e) { cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking); }
-    ~ContextImpl() override { if (stream_) cudaStreamDestroy(stream_); }
+    explicit ContextImpl(EngineImpl* e);
+    ~ContextImpl() override
+    {
+        if (stream_) cudaStreamDestroy(stream_);
+        if (arena_) cudaFree(arena_);
+        if (workspace_) cudaFree(workspace_);
+    }
     bool execute(int batchSize, void** bindings) override;
     bool enqueue(int batchSize, void** bindings, cudaStream_t stream, cudaEvent_t* inputConsumed) override;
     void setDebugSync(bool sync) override { debug_sync_ = sync; }
@@ -446,6 +451,11 @@ private:
     bool run(int batchSize, void** bindings, cudaStream_t stream, bool profile);
     EngineImpl* engine_;
     cudaStream_t stream_ = nullptr;
+    // Activations and scratch belong to the CONTEXT (as in TensorRT): several contexts of one engine may run concurrently
+    // on different streams without touching each other's intermediate tensors.
+    void* arena_ = nullptr;
+    void* workspace_ = nullptr;
+    bool alloc_ok_ = true;
     IProfiler* profiler_ = nullptr;
     bool debug_sync_ = false;
 };
@@ -459,8 +469,6 @@ public:
         for (auto* p : conv2d_plans_) rt_conv2d_destroy(p);
         for (auto* p : conv3d_plans_) rt_conv3d_destroy(p);
         for (auto* p : cvconv_plans_) rt_costvol_conv3d_destroy(p);
-        if (arena_) cudaFree(arena_);
-        if (workspace_) cudaFree(workspace_);
     }
     int getNbBindings() const override { return static_cast<int>(bindings_.size()); }
     int getBindingIndex(const char* name) const override
@@ -502,10 +510,8 @@ public:
     std::vector<TensorSlot> slots_;
     std::vector<int> bindings_;          // binding index -> tensor id
     std::vector<Step> steps_;
-    void* arena_ = nullptr;
-    size_t arena_bytes_ = 0;
-    void* workspace_ = nullptr;
-    size_t workspace_bytes_ = 0;
+    size_t arena_bytes_ = 0;             // per execution context
+    size_t workspace_bytes_ = 0;         // per execution context
     std::vector<IPlugin*> configured_plugins_;
     std::vector<rt_conv2d_plan*> conv2d_plans_;
     std::vector<rt_conv3d_plan*> conv3d_plans_;
@@ -519,6 +525,14 @@ private:
 };
 
 const ICudaEngine& ContextImpl::getEngine() const { return *engine_; }
+
+ContextImpl::ContextImpl(EngineImpl* e) : engine_(e)
+{
+    alloc_ok_ = cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking) == cudaSuccess;
+    if (alloc_ok_ && e->arena_bytes_ > 0) alloc_ok_ = cudaMalloc(&arena_, e->arena_bytes_) == cudaSuccess;
+    if (alloc_ok_ && e->workspace_bytes_ > 0) alloc_ok_ = cudaMalloc(&workspace_, e->workspace_bytes_) == cudaSuccess;
+    if (!alloc_ok_) logMsg(e->log_, ILogger::Severity::kERROR, "createExecutionContext: cudaMalloc of the activation arena / workspace failed");
+}
 
 // Weight helpers ---------------------------------------------------------------------------------------------------
 float weightScalar(const Weights& w, float dflt)
@@ -576,9 +590,11 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
         auto* op = dynamic_cast<IRedtailOp*>(d.plugin);
         return op ? &op->opInfo() : nullptr;
     };
+    // An ELU plugin declared kHALF (the fp16 builders, resnet18_2D_513x257_net.cpp with data_type = kHALF) fuses as well:
+    // the epilogue evaluates it in fp32, which is at least as accurate as the fp16 tensor the plugin would round to.
     auto isFp32Elu = [&](int li) {
         const OpInfo* o = li >= 0 ? opOf(li) : nullptr;
-        return o && o->kind == OpKind::kElu && o->data_type == DataType::kFLOAT;
+        return o && o->kind == OpKind::kElu && (o->data_type == DataType::kFLOAT || o->data_type == DataType::kHALF);
     };
 
     std::vector<bool> done(nl, false);
@@ -749,8 +765,9 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                         if (nxt >= 0 && net.layers_[nxt]->d.kind == LKind::kEltwise) {
                             LayerData& e = net.layers_[nxt]->d;
                             TensorImpl* other = e.in[0] == out ? e.in[1] : e.in[0];
-                            // the skip tensor must already be produced (it is: layers are in topological order)
-                            if (other != out) {
+                            // The add moves up to this layer's position, so the skip tensor must exist by then: a network
+                            // input, or produced by an EARLIER layer (topological order alone only puts it before the add).
+                            if (other != out && (other->is_input || (other->producer >= 0 && other->producer < li))) {
                                 skip_id = other->id;
                                 done[nxt] = true; out = e.out[0]; st.name += " + " + e.name;
                                 nxt = soleConsumer(out);
@@ -796,14 +813,47 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                     }
                 }
                 // ---- cost volume / Transform: remember them, the layout pass may rewrite or drop them ------------------
-                if (fusion && op && op->kind == OpKind::kCostVolume && op->cv_type == redtail::tensorrt::CostVolumeType::kDefault &&
-                    op->data_type == DataType::kFLOAT) {
+                if (fusion && op && op->kind == OpKind::kCostVolume && op->cv_type == redtail::tensorrt::CostVolumeType::kDefault) {
                     st.costvol_c = d.in[0]->dims.d[0];
                     st.costvol_h = d.in[0]->dims.d[1];
                     st.costvol_w = d.in[0]->dims.d[2];
                     st.costvol_d = op->max_disparity;
                 }
                 if (fusion && op && op->kind == OpKind::kTransform) st.is_transform = true;
+                // ---- redtail plugins declared kHALF (the fp16 builders: resnet18_2D_513x257_net.cpp with data_type = kHALF) ----
+                // The graph's tensors are fp32; instead of wrapping the plugin in fp32<->fp16 reformat passes (what TensorRT
+                // does, and what rounds every activation to fp16) the engine runs the same kernel on the fp32 tensors: one
+                // pass instead of three, and the fp16 configuration keeps fp32 activations (only its WEIGHTS are fp16).
+                if (fusion && op && op->data_type == DataType::kHALF &&
+                    (op->kind == OpKind::kElu || op->kind == OpKind::kCostVolume || op->kind == OpKind::kSoftargmax)) {
+                    const int out_id = d.out[0]->id;
+                    st.out.push_back(out_id);
+                    if (op->kind == OpKind::kElu) {
+                        const int in_id = d.in[0]->id;
+                        const int64_t elems = static_cast<int64_t>(slots_[in_id].elems);
+                        st.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                            return rt_elu(RT_F32, ptr(in_id), ptr(out_id), elems * batch, s);
+                        };
+                    } else if (op->kind == OpKind::kCostVolume) {
+                        const int l = d.in[0]->id, r = d.in[1]->id;
+                        const int c = d.in[0]->dims.d[0], h = d.in[0]->dims.d[1], w = d.in[0]->dims.d[2], dd = op->max_disparity;
+                        const bool corr = op->cv_type == redtail::tensorrt::CostVolumeType::kCorrelation;
+                        st.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                            return corr ? rt_corr_cost_volume(RT_F32, ptr(l), ptr(r), ptr(out_id), batch, c, h, w, dd, s)
+                                        : rt_cost_volume(RT_F32, ptr(l), ptr(r), ptr(out_id), batch, c, h, w, dd, s);
+                        };
+                    } else {
+                        const int in_id = d.in[0]->id;
+                        const Dims& id = d.in[0]->dims;
+                        const int dd = id.d[0];
+                        const int64_t hw = static_cast<int64_t>(slots_[in_id].elems) / dd;
+                        const int is_min = op->sm_type == redtail::tensorrt::SoftargmaxType::kMin ? 1 : 0;
+                        st.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                            return rt_softargmax(RT_F32, is_min, ptr(in_id), ptr(out_id), batch, dd, hw, s);
+                        };
+                    }
+                    break;
+                }
                 // ---- generic plugin protocol ---------------------------------------------------------------------
                 std::vector<Dims> ind, outd;
                 for (auto* t : d.in) ind.push_back(t->dims);
@@ -1130,8 +1180,6 @@ bool EngineImpl::planMemory()
     }
     workspace_bytes_ = 0;
     for (auto& s : steps_) workspace_bytes_ = std::max(workspace_bytes_, s.workspace);
-    if (arena_bytes_ > 0 && cudaMalloc(&arena_, arena_bytes_) != cudaSuccess) return fail("cudaMalloc of the activation arena failed");
-    if (workspace_bytes_ > 0 && cudaMalloc(&workspace_, workspace_bytes_) != cudaSuccess) return fail("cudaMalloc of the workspace failed");
     logMsg(log_, ILogger::Severity::kINFO, "engine: " + std::to_string(steps_.size()) + " steps, activation arena " +
                                                std::to_string(arena_bytes_ >> 20) + " MiB, workspace " + std::to_string(workspace_bytes_ >> 20) + " MiB");
     return true;
@@ -1144,11 +1192,15 @@ bool ContextImpl::run(int batchSize, void** bindings, cudaStream_t stream, bool 
         logMsg(e.log_, ILogger::Severity::kERROR, "execute: invalid batch size or bindings");
         return false;
     }
+    if (!alloc_ok_) {
+        logMsg(e.log_, ILogger::Severity::kERROR, "execute: this context has no activation memory (allocation failed at creation)");
+        return false;
+    }
     std::function<void*(int)> ptr = [&](int id) -> void* {
         while (e.slots_[id].alias_of >= 0) id = e.slots_[id].alias_of;
         const TensorSlot& s = e.slots_[id];
         if (s.binding >= 0) return bindings[s.binding];
-        return static_cast<char*>(e.arena_) + s.offset;
+        return static_cast<char*>(arena_) + s.offset;
     };
     std::vector<cudaEvent_t> ev;
     if (profile) {
@@ -1158,7 +1210,7 @@ bool ContextImpl::run(int batchSize, void** bindings, cudaStream_t stream, bool 
     }
     bool ok = true;
     for (size_t i = 0; i < e.steps_.size(); ++i) {
-        const int rc = e.steps_[i].run(batchSize, ptr, e.workspace_, stream);
+        const int rc = e.steps_[i].run(batchSize, ptr, workspace_, stream);
         if (rc != 0) {
             logMsg(e.log_, ILogger::Severity::kERROR, e.steps_[i].name + ": enqueue failed with status " + std::to_string(rc));
             ok = false;
@@ -1181,7 +1233,13 @@ bool ContextImpl::run(int batchSize, void** bindings, cudaStream_t stream, bool 
 
 bool ContextImpl::execute(int batchSize, void** bindings)
 {
-    // The caller's copies ran on the legacy default stream (cudaMemcpy): they are complete by the time we are called.
+    // The reference's callers upload with plain cudaMemcpy (pageable memory: the call may return before the DMA has
+    // finished) or queue work on the legacy default stream; a non-blocking stream is not ordered against either, so wait
+    // for the legacy stream first (free when nothing is pending).
+    if (cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) {
+        logMsg(engine_->log_, ILogger::Severity::kERROR, "execute: pending work on the default stream failed");
+        return false;
+    }
     const bool ok = run(batchSize, bindings, stream_, profiler_ != nullptr);
     const cudaError_t err = cudaStreamSynchronize(stream_);
     if (err != cudaSuccess) {

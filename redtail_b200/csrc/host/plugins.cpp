@@ -26,15 +26,25 @@ struct ByteWriter {
     std::string buf;
     template <typename T> void put(T v) { buf.append(reinterpret_cast<const char*>(&v), sizeof(T)); }
 };
+// A plan is untrusted input: a short or inconsistent blob clears `ok` (the factory then returns nullptr and
+// deserializeCudaEngine reports the error) instead of reading past the buffer or the Dims array.
 struct ByteReader {
-    const char* p; size_t left;
+    const char* p; size_t left; bool ok = true;
     template <typename T> T get() {
         T v{};
-        assert(left >= sizeof(T));
+        if (left < sizeof(T)) { ok = false; left = 0; return v; }
         memcpy(&v, p, sizeof(T));
         p += sizeof(T); left -= sizeof(T);
         return v;
     }
+    void dims(Dims& d) {
+        d = Dims{};
+        const int32_t n = get<int32_t>();
+        if (n < 0 || n > Dims::MAX_DIMS) { ok = false; return; }
+        d.nbDims = n;
+        for (int i = 0; i < n; i++) d.d[i] = get<int32_t>();
+    }
+    bool done() const { return ok && left == 0; }
 };
 
 void logDims(ILogger& log, const std::string& name, const char* what, Dims d)
@@ -60,11 +70,10 @@ public:
         info_.kind = OpKind::kElu; info_.name = name;
         info_.data_type = static_cast<DataType>(r.get<int32_t>());
         format_ = static_cast<PluginFormat>(r.get<uint8_t>());
-        in_dims_.nbDims = r.get<int32_t>();
-        assert(in_dims_.nbDims >= 0 && in_dims_.nbDims <= Dims::MAX_DIMS);
-        for (int i = 0; i < in_dims_.nbDims; i++) in_dims_.d[i] = r.get<int32_t>();
-        assert(r.left == 0);
+        r.dims(in_dims_);
+        valid_ = r.done() && (info_.data_type == DataType::kFLOAT || info_.data_type == DataType::kHALF);
     }
+    bool valid() const { return valid_; }
     const OpInfo& opInfo() const override { return info_; }
 
     bool supportsFormat(DataType type, PluginFormat format) const override
@@ -115,6 +124,7 @@ private:
     OpInfo info_;
     PluginFormat format_ = PluginFormat::kNCHW;
     Dims in_dims_{};
+    bool valid_ = true;       // false: constructed from a malformed serialised blob
     ILogger& log_;
 };
 
@@ -141,12 +151,11 @@ public:
         format_ = static_cast<PluginFormat>(r.get<uint8_t>());
         info_.cv_type = static_cast<CostVolumeType>(r.get<int32_t>());
         info_.max_disparity = r.get<int32_t>();
-        in_dims_.nbDims = r.get<int32_t>();
-        for (int i = 0; i < in_dims_.nbDims; i++) in_dims_.d[i] = r.get<int32_t>();
-        out_dims_.nbDims = r.get<int32_t>();
-        for (int i = 0; i < out_dims_.nbDims; i++) out_dims_.d[i] = r.get<int32_t>();
-        assert(r.left == 0);
+        r.dims(in_dims_);
+        r.dims(out_dims_);
+        valid_ = r.done() && info_.max_disparity > 0 && (info_.data_type == DataType::kFLOAT || info_.data_type == DataType::kHALF);
     }
+    bool valid() const { return valid_; }
     const OpInfo& opInfo() const override { return info_; }
 
     bool supportsFormat(DataType type, PluginFormat format) const override
@@ -210,6 +219,7 @@ private:
     OpInfo info_;
     PluginFormat format_ = PluginFormat::kNCHW;
     Dims in_dims_{}, out_dims_{};
+    bool valid_ = true;       // false: constructed from a malformed serialised blob
     ILogger& log_;
 };
 
@@ -232,12 +242,11 @@ public:
         info_.kind = OpKind::kSoftargmax; info_.name = name;
         info_.data_type = static_cast<DataType>(r.get<int32_t>());
         info_.sm_type = static_cast<SoftargmaxType>(r.get<int32_t>());
-        in_dims_.nbDims = r.get<int32_t>();
-        for (int i = 0; i < in_dims_.nbDims; i++) in_dims_.d[i] = r.get<int32_t>();
-        out_dims_.nbDims = r.get<int32_t>();
-        for (int i = 0; i < out_dims_.nbDims; i++) out_dims_.d[i] = r.get<int32_t>();
-        assert(r.left == 0);
+        r.dims(in_dims_);
+        r.dims(out_dims_);
+        valid_ = r.done() && (info_.data_type == DataType::kFLOAT || info_.data_type == DataType::kHALF);
     }
+    bool valid() const { return valid_; }
     const OpInfo& opInfo() const override { return info_; }
 
     bool supportsFormat(DataType type, PluginFormat format) const override
@@ -295,6 +304,7 @@ private:
     }
     OpInfo info_;
     Dims in_dims_{}, out_dims_{};
+    bool valid_ = true;       // false: constructed from a malformed serialised blob
     ILogger& log_;
 };
 
@@ -646,7 +656,13 @@ public:
     }
     IPlugin* deserializeEluPlugin(const char* name, const void* data, size_t size) override
     {
-        return keep(new EluPlugin(name, data, size, log_));
+        auto* p = new EluPlugin(name, data, size, log_);
+        if (!p->valid()) {
+            log_.log(ILogger::Severity::kERROR, (std::string(name ? name : "") + ": malformed serialised EluPlugin").c_str());
+            delete p;
+            return nullptr;
+        }
+        return keep(p);
     }
     IPlugin* createCostVolumePlugin(DataType data_type, CostVolumeType cv_type, int max_disparity, std::string name) override
     {
@@ -654,7 +670,13 @@ public:
     }
     IPlugin* deserializeCostVolumePlugin(const char* name, const void* data, size_t size) override
     {
-        return keep(new CostVolumePlugin(name, data, size, log_));
+        auto* p = new CostVolumePlugin(name, data, size, log_);
+        if (!p->valid()) {
+            log_.log(ILogger::Severity::kERROR, (std::string(name ? name : "") + ": malformed serialised CostVolumePlugin").c_str());
+            delete p;
+            return nullptr;
+        }
+        return keep(p);
     }
     IPlugin* createConv3DPlugin(Conv3DType conv_type, Dims kernel_dims, Dims stride_dims, Dims pad_start_dims,
                                 Dims pad_end_dims, Weights kernel_weights, Weights bias_weights, std::string name) override
@@ -687,7 +709,13 @@ public:
     }
     IPlugin* deserializeSoftargmaxPlugin(const char* name, const void* data, size_t size) override
     {
-        return keep(new SoftargmaxPlugin(name, data, size, log_));
+        auto* p = new SoftargmaxPlugin(name, data, size, log_);
+        if (!p->valid()) {
+            log_.log(ILogger::Severity::kERROR, (std::string(name ? name : "") + ": malformed serialised SoftargmaxPlugin").c_str());
+            delete p;
+            return nullptr;
+        }
+        return keep(p);
     }
 
 private:
@@ -780,7 +808,7 @@ StereoDnnPluginFactory::StereoDnnPluginFactory(IPluginContainer& container) : co
 
 IPlugin* StereoDnnPluginFactory::createPlugin(const char* layerName, const void* serialData, size_t serialLength)
 {
-    assert(serialLength >= sizeof(int32_t));
+    if (serialData == nullptr || serialLength < sizeof(int32_t)) return nullptr;
     int32_t tag;
     memcpy(&tag, serialData, sizeof(tag));
     const char* rest = static_cast<const char*>(serialData) + sizeof(tag);
@@ -804,7 +832,12 @@ IPlugin* StereoDnnPluginFactory::createPlugin(const char* layerName, const void*
             const DataType wt = static_cast<DataType>(r.get<int32_t>());
             const int64_t kcount = r.get<int64_t>(), bcount = r.get<int64_t>();
             const size_t es = wt == DataType::kHALF ? 2 : 4;
-            assert(kcount > 0 && bcount >= 0 && r.left == static_cast<size_t>(kcount + bcount) * es);
+            if (!r.ok || (wt != DataType::kHALF && wt != DataType::kFLOAT) || kcount <= 0 || bcount < 0 ||
+                r.left != static_cast<size_t>(kcount + bcount) * es)
+                return nullptr;
+            int64_t kvol = 1;
+            for (int i = 0; i < 5; i++) { if (kd.d[i] <= 0) return nullptr; kvol *= kd.d[i]; }
+            if (kvol != kcount) return nullptr;
             Weights kw{wt, r.p, kcount};
             Weights bw{wt, bcount > 0 ? r.p + kcount * es : nullptr, bcount};
             IPlugin* p = tr ? container_.createConv3DTransposePlugin(Conv3DType::kTensorFlow, kd, DimsNCHW(od[0], od[1], od[2], od[3]),
@@ -819,23 +852,26 @@ IPlugin* StereoDnnPluginFactory::createPlugin(const char* layerName, const void*
             ByteReader r{rest, rest_len};
             Permutation perm{};
             for (int i = 0; i < 4; i++) perm.order[i] = r.get<int32_t>();
+            if (!r.done()) return nullptr;
             return container_.createTransformPlugin(perm, layerName);
         }
         case PluginType::kPadding: {
             ByteReader r{rest, rest_len};
-            return container_.createPaddingPlugin(DimsNCHW(0, 0, 0, 0), DimsNCHW(r.get<int32_t>(), 0, 0, 0), layerName);
+            const int planes = r.get<int32_t>();
+            if (!r.done() || planes < 0) return nullptr;
+            return container_.createPaddingPlugin(DimsNCHW(0, 0, 0, 0), DimsNCHW(planes, 0, 0, 0), layerName);
         }
         case PluginType::kSlice: {
             ByteReader r{rest, rest_len};
             int d[4];
             for (int i = 0; i < 4; i++) d[i] = r.get<int32_t>();
             const int s0 = r.get<int32_t>(), s1 = r.get<int32_t>();
+            if (!r.done()) return nullptr;
             return container_.createSlicePlugin(DimsNCHW(d[0], d[1], d[2], d[3]), DimsNCHW(s0, 0, 0, 0),
                                                 DimsNCHW(s1, d[1], d[2], d[3]), layerName);
         }
     }
-    assert(false);
-    return nullptr;
+    return nullptr;       // unknown tag
 }
 
 } }

@@ -87,6 +87,9 @@ struct TcParams {
     int ncols;               // columns that map to an output: cpc << (ld + lh + lw)
     int lc, ld, lh, lw;      // log2 of: channels per parity class, merged parities along D, H, W
     int split;               // 1: hi/lo operands (RT_PREC_FP32), 0: hi only
+    int wlo;                 // split mode: 1 = weight tiles are [W_hi ; W_lo] (nb = 2 * cout_pad), 0 = every weight is exactly
+                             // representable in fp16 (the reference's trt_weights_fp16.bin) so the A_hi x W_lo product is
+                             // identically zero and is not issued: two products (A_hi x W, A_lo x W) instead of three
     int stages;
     int chunk_kb;            // K blocks (stages) accumulated in TMEM before the epilogue adds them up in fp32 registers
     int chunk_rows;          // < gr: a chunk is closed after this many filter rows inside a stage (chunk_kb == 1)
@@ -110,16 +113,16 @@ struct TcParams {
 // One CTA handles 64 consecutive w of one (n, d, h) row for all C channels through a padded smem transpose.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-pack_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int d_ext, int c_ext,
+pack_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int d_ext, int c_src, int c_ext,
                   int h_ext, int w_ext, long long s_n, long long s_d, long long s_c, long long o_sn) {
-    extern __shared__ float tile[];                    // [c_ext][65]
+    extern __shared__ float tile[];                    // [c_ext][65]; channels c_src .. c_ext-1 are zero padding
     const int w0 = blockIdx.x * 64;
     const int h = blockIdx.y;
     const int d = blockIdx.z % d_ext, n = blockIdx.z / d_ext;
     const float* src = x + n * s_n + d * s_d + static_cast<long long>(h) * w_ext;
     for (int i = threadIdx.x; i < c_ext * 64; i += 256) {
         const int c = i >> 6, w = i & 63;
-        tile[c * 65 + w] = (w0 + w < w_ext) ? __ldg(src + c * s_c + w0 + w) : 0.f;
+        tile[c * 65 + w] = (w0 + w < w_ext && c < c_src) ? __ldg(src + c * s_c + w0 + w) : 0.f;
     }
     __syncthreads();
     const long long pix0 = (static_cast<long long>(d) * h_ext + h) * w_ext + w0;      // within the sample
@@ -253,8 +256,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             const uint64_t desc_b_hi = (static_cast<uint64_t>(((8u * pitch) >> 4) | (1u << 14) | (swz << 29))) << 32;
             // A in hs2 mode: the next 8-row group (= next patch row, tw = 8) is two box rows further
             const uint64_t desc_hi = (static_cast<uint64_t>((((p.hs2 ? 16u : 8u) * pitch) >> 4) | (1u << 14) | (swz << 29))) << 32;
-            const uint32_t idesc_full = umma_idesc_f16(kTileM, kAccCols);
             const uint32_t idesc_half = umma_idesc_f16(kTileM, kCoutPad);
+            const uint32_t idesc_full = (SPLIT && !p.wlo) ? idesc_half : umma_idesc_f16(kTileM, kAccCols);
             const uint32_t ring_addr = smem_u32(ring);
             const uint32_t stage_bytes = p.stage_bytes, a_bytes = p.a_bytes;
             const int kc16 = p.kc >> 4, stages = p.stages, chunk_kb = p.chunk_kb, chunk_rows = p.chunk_rows, ncb = p.ncb, gr = p.gr;
@@ -488,7 +491,8 @@ struct TcPlan {
     TcParams p{};
     __half* w_dev = nullptr;          // packed weights [taps][ncb][nb][kc]
     CUtensorMap map_w{};
-    int cin = 0;
+    int cin = 0;                      // channels of the packed activations (K-block multiple)
+    int cin_src = 0;                  // channels of the caller's tensor (<= cin; the rest is zero padding)
     int in_d = 0, in_h = 0, in_w = 0; // input spatial extent
     long long in_sn = 0, in_sd = 0, in_sc = 0;   // dense fp32 input strides (sample, depth, channel)
     size_t in_elems = 0;              // per sample, = D*H*W*C
@@ -511,12 +515,17 @@ float h2f_bits(uint16_t b) {
 
 }  // namespace
 
+// Input channels as the kernel sees them: 16, 32 or a multiple of 64.
+static int tc_padded_cin(int cin) { return cin <= 16 ? 16 : (cin <= 32 ? 32 : (cin + 63) / 64 * 64); }
+
 // Coverage of the tensor-core tiles (shape only; no device work).
 bool tc_shape_supported(const rt_conv3d_desc& d) {
     const int cin = d.transposed ? d.k : d.c, cout = d.transposed ? d.c : d.k;
-    if (cin % 16 != 0 || cin < 16) return false;
-    if (cin > 64 && cin % 64 != 0) return false;
-    if (cin < 64 && cin != 16 && cin != 32) return false;
+    // K blocks are 16, 32 or 64 channels wide.  A dense fp32 input is re-laid out by the pack pass anyway, which zero-pads
+    // the channels up to the next block size (so the reference's 1..8-channel unit-test tensors run on the tensor cores
+    // too); a split16 input is consumed in place and must already have a block-sized channel count.
+    if (cin < 1) return false;
+    if (d.in_layout == RT_LAYOUT_SPLIT16 && tc_padded_cin(cin) != cin) return false;
     if (cout > 128 || cout < 1) return false;
     if (d.v > 3 || d.r > 3 || d.s > 3) return false;
     for (int i = 0; i < 3; ++i)
@@ -529,7 +538,8 @@ bool tc_shape_supported(const rt_conv3d_desc& d) {
 int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::vector<float>& /*bias*/) {
     const rt_conv3d_desc& d = plan->desc;
     const bool tr = d.transposed != 0;
-    const int cin = plan->cin, cout = plan->cout;
+    const int cin_src = plan->cin, cout = plan->cout;
+    const int cin = tc_padded_cin(cin_src);            // zero-padded by the pack pass (weights of the padding are zero too)
     if (!tc_shape_supported(d)) return RT_ERR_UNSUPPORTED;
     const bool out_split = d.out_layout == RT_LAYOUT_SPLIT16;
     // Channels per parity class (power of two) and which stride-2 output parities are merged into GEMM-N.
@@ -553,7 +563,15 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     int cout_pad = 16;
     while (cout_pad < ncols) cout_pad *= 2;
     const bool split = d.precision == RT_PREC_FP32;
-    const int nb = split ? 2 * cout_pad : cout_pad;
+    // fp16-exact weights (an fp16 weight file, or fp32 values that happen to be representable): W_lo == 0 everywhere.
+    bool wlo = false;
+    if (split && !getenv("REDTAIL_TC_NO_WLO_SKIP")) {
+        for (float v : w) {
+            const float c = v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v);
+            if (h2f_bits(f2h_bits(c)) != c) { wlo = true; break; }
+        }
+    } else wlo = split;
+    const int nb = (split && wlo) ? 2 * cout_pad : cout_pad;
     if (nb > 256) return RT_ERR_UNSUPPORTED;
     if (d.v > 3 || d.r > 3 || d.s > 3) return RT_ERR_UNSUPPORTED;
     for (int i = 0; i < 3; ++i)
@@ -563,7 +581,9 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     TcPlan* t = new TcPlan();
     TcParams& p = t->p;
     t->cin = cin;
+    t->cin_src = cin_src;
     p.split = split;
+    p.wlo = wlo ? 1 : 0;
     p.kc = cin >= 64 ? 64 : cin;
     p.ncb = cin / p.kc;
     p.cout = cout; p.cout_pad = cout_pad; p.nb = nb;
@@ -572,7 +592,7 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     int out_ext[3];
     if (!tr) {
         t->in_d = d.in_dims[0]; t->in_h = d.in_dims[2]; t->in_w = d.in_dims[3];
-        t->in_sd = static_cast<long long>(cin) * t->in_h * t->in_w;      // input [D,C,H,W]
+        t->in_sd = static_cast<long long>(cin_src) * t->in_h * t->in_w;  // input [D,C,H,W]
         t->in_sc = static_cast<long long>(t->in_h) * t->in_w;
         out_ext[0] = d.out_dims[1]; out_ext[1] = d.out_dims[2]; out_ext[2] = d.out_dims[3];
         for (int i = 0; i < 3; ++i) { p.in_s[i] = d.stride[i]; p.out_s[i] = 1; }
@@ -590,8 +610,8 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
         p.out_sd = cout * plane; p.out_sc = plane;                                      // [Dx,C,Hx,Wx]
         p.out_sn = static_cast<long long>(out_ext[0]) * cout * plane;
     }
-    t->in_sn = static_cast<long long>(cin) * t->in_d * t->in_h * t->in_w;
-    t->in_elems = static_cast<size_t>(t->in_sn);
+    t->in_sn = static_cast<long long>(cin_src) * t->in_d * t->in_h * t->in_w;              // caller's tensor
+    t->in_elems = static_cast<size_t>(cin) * t->in_d * t->in_h * t->in_w;                   // packed planes
     p.out_d = out_ext[0]; p.out_h = out_ext[1]; p.out_w = out_ext[2];
 
     p.ncols = ncols;
@@ -752,14 +772,14 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
                 ok = ok && tp[i] >= 0;
             }
             if (!ok) continue;
-            for (int kin = 0; kin < cin; ++kin) {
+            for (int kin = 0; kin < cin_src; ++kin) {
                 const int kk = tr ? kin : ch, cc = tr ? ch : kin;       // KVCRS indices
                 float val = w[(((static_cast<size_t>(kk) * d.v + tp[0]) * d.c + cc) * d.r + tp[1]) * d.s + tp[2]];
                 val = val > 65504.f ? 65504.f : (val < -65504.f ? -65504.f : val);
                 const size_t base = ((static_cast<size_t>(ti) * p.ncb + kin / p.kc) * nb) * p.kc + (kin % p.kc);
                 const uint16_t hb = f2h_bits(val);
                 pk[base + static_cast<size_t>(col) * p.kc] = hb;
-                if (split) pk[base + static_cast<size_t>(cout_pad + col) * p.kc] = f2h_bits((val - h2f_bits(hb)) * 2048.f);
+                if (wlo) pk[base + static_cast<size_t>(cout_pad + col) * p.kc] = f2h_bits((val - h2f_bits(hb)) * 2048.f);
             }
         }
     }
@@ -865,7 +885,7 @@ int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const f
         if (static_cast<long long>(n) * t->in_d > 65535 || t->in_h > 65535) return RT_ERR_UNSUPPORTED;
         dim3 grid((t->in_w + 63) / 64, t->in_h, n * t->in_d);
         const size_t sm = static_cast<size_t>(t->cin) * 65 * sizeof(float);
-        pack_split_kernel<<<grid, 256, sm, s>>>(x, whi, whi + t->in_elems, t->in_d, t->cin, t->in_h, t->in_w, t->in_sn,
+        pack_split_kernel<<<grid, 256, sm, s>>>(x, whi, whi + t->in_elems, t->in_d, t->cin_src, t->cin, t->in_h, t->in_w, t->in_sn,
                                                 t->in_sd, t->in_sc, static_cast<long long>(2 * t->in_elems));
         note_launch("conv3d_pack_split");
         RT_CHECK_LAUNCH();
@@ -917,7 +937,7 @@ int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const f
         default: return RT_ERR_UNSUPPORTED;
     }
 #undef RT_LAUNCH_UMMA
-    note_launch(p.split ? "conv3d_umma_fp16x2split" : "conv3d_umma_fp16");
+    note_launch(p.split ? (p.wlo ? "conv3d_umma_fp16x2split" : "conv3d_umma_fp16x2split_w16") : "conv3d_umma_fp16");
     RT_CHECK_LAUNCH();
     return RT_OK;
 }

@@ -174,7 +174,7 @@ int rt_dense_to_split16(const void* x, void* y, int n, int d, int c, int h, int 
 
 int rt_split16_to_dense(const void* x, void* y, int n, int d, int c, int h, int w, void* stream) {
     if (!x || !y || n < 0 || d <= 0 || c <= 0 || h <= 0 || w <= 0) return RT_ERR_ARG;
-    if (c > 512 || static_cast<long long>(n) * d > 65535 || h > 65535) return RT_ERR_UNSUPPORTED;
+    if (c % 8 != 0 || c > 512 || static_cast<long long>(n) * d > 65535 || h > 65535) return RT_ERR_UNSUPPORTED;
     if (n == 0) return RT_OK;
     const size_t smem = static_cast<size_t>(c) * 65 * sizeof(float);
     if (smem > 48 * 1024) RT_CUDA(cudaFuncSetAttribute(split16_to_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -25,7 +25,9 @@ __device__ __forceinline__ void online_update(Partial& p, float v, float idx) {
         p.ws = p.ws * sc + idx;
         p.m = v;
     } else {
-        const float e = expf(v - p.m);
+        // v == -inf while the running max is still -inf would give expf(NaN); such an entry has weight 0
+        // (the cuDNN SOFTMAX_ACCURATE pass this replaces returns finite weights for -inf inputs).
+        const float e = (v == -INFINITY) ? 0.f : expf(v - p.m);
         p.s += e;
         p.ws += e * idx;
     }

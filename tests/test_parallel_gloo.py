@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from redtail_b200.parallel import shard_range, gather_disparities
+from redtail_b200.parallel import OverlappedGather, shard_range, gather_disparities
 
 
 def _free_port():
@@ -25,7 +25,14 @@ def _worker(rank, world, port, total, q):
     # fake "disparity maps": pair i is filled with the value i
     local = torch.stack([torch.full((5, 7), float(i)) for i in range(b, e)])
     full = gather_disparities(local)
-    q.put((rank, (b, e), full[:, 0, 0].tolist()))
+    # the rotating-buffer variant bench.py uses (synchronous on a CPU group): three steps through two buffers
+    g = OverlappedGather(tuple(local.shape), local.dtype, "cpu", depth=2)
+    rot = []
+    for step in range(3):
+        g.next_buffer().copy_(local + 100.0 * step)
+        rot.append(g.submit()[:, 0, 0].tolist())
+    g.flush()
+    q.put((rank, (b, e), full[:, 0, 0].tolist(), rot))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -52,10 +59,16 @@ def test_two_rank_gather_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, span, order in res:
+    for rank, span, order, rot in res:
         assert order == [float(i) for i in range(total)], (rank, order)     # every rank sees all pairs in batch order
+        for step, got in enumerate(rot):
+            assert got == [float(i) + 100.0 * step for i in range(total)], (rank, step, got)
 
 
 def test_single_process_is_identity():
     x = torch.randn(2, 3, 4)
     assert gather_disparities(x) is x
+    g = OverlappedGather((2, 3, 4), torch.float32, "cpu")
+    buf = g.next_buffer()
+    buf.copy_(x)
+    assert torch.equal(g.submit(), x)

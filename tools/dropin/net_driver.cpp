@@ -3,7 +3,9 @@
 // sample_app/main.cpp:176-315 minus OpenCV (raw CHW float32 .bin images in, raw float32 disparity out).
 // Test infrastructure (tools/dropin); built only where /root/reference exists.
 //
-//   nvstereo_net_driver <nvsmall|nvtiny|resnet18|resnet18_2D> <width> <height> <weights.bin> <left.bin> <right.bin> <out.bin> [profile|plan|dump]
+//   nvstereo_net_driver <nvsmall|nvtiny|resnet18|resnet18_2D> <width> <height> <weights.bin> <left.bin> <right.bin> <out.bin> [profile|plan|dump] [fp16]
+//   fp16: <weights.bin> is a trt_weights_fp16.bin; the weights reach the builders as DataType::kHALF, ResNet18_2D gets
+//         data_type = kHALF and the builder half2 mode, the other nets keep kFLOAT plugins -- sample_app/main.cpp:224-256.
 //   plan: the engine is serialised, destroyed together with the weights and the plugin container, and re-created with
 //         IRuntime::deserializeCudaEngine + StereoDnnPluginFactory (sample_app/main.cpp:207-220,270-275) before it runs.
 #include <NvInfer.h>
@@ -46,7 +48,7 @@ static std::vector<float> readBin(const char* path)
     return v;
 }
 
-static std::unordered_map<std::string, Weights> readWeights(const char* path, std::vector<std::vector<float>>& keep)
+static std::unordered_map<std::string, Weights> readWeights(const char* path, std::vector<std::vector<float>>& keep, bool fp16)
 {
     std::unordered_map<std::string, Weights> w;
     std::ifstream f(path, std::ios::binary);
@@ -56,9 +58,9 @@ static std::unordered_map<std::string, Weights> readWeights(const char* path, st
         std::getline(f, name, '\0');
         uint32_t count = 0;
         f.read(reinterpret_cast<char*>(&count), 4);
-        keep.emplace_back(count);
-        f.read(reinterpret_cast<char*>(keep.back().data()), count * 4ull);
-        w[name] = Weights{DataType::kFLOAT, keep.back().data(), count};
+        keep.emplace_back(fp16 ? (count + 1) / 2 : count);           // fp16 payloads are stored two per float slot
+        f.read(reinterpret_cast<char*>(keep.back().data()), count * (fp16 ? 2ull : 4ull));
+        w[name] = Weights{fp16 ? DataType::kHALF : DataType::kFLOAT, keep.back().data(), count};
     }
     return w;
 }
@@ -70,7 +72,10 @@ int main(int argc, char** argv)
     const int w = atoi(argv[2]), h = atoi(argv[3]);
     Log log;
     std::vector<std::vector<float>> keep;
-    auto weights = readWeights(argv[4], keep);
+    bool fp16 = false;
+    for (int i = 8; i < argc; ++i) fp16 = fp16 || !strcmp(argv[i], "fp16");
+    const DataType data_type = fp16 ? DataType::kHALF : DataType::kFLOAT;
+    auto weights = readWeights(argv[4], keep, fp16);
     auto left = readBin(argv[5]), right = readBin(argv[6]);
     if (left.size() != size_t(3) * h * w || right.size() != left.size()) { fprintf(stderr, "image size mismatch\n"); return 2; }
 
@@ -80,20 +85,21 @@ int main(int argc, char** argv)
     if (model == "nvsmall") net = createNVSmall1025x321Network(*builder, *container, DimsCHW{3, h, w}, weights, DataType::kFLOAT, log);
     else if (model == "nvtiny") net = createNVTiny513x161Network(*builder, *container, DimsCHW{3, h, w}, weights, DataType::kFLOAT, log);
     else if (model == "resnet18") net = createResNet18_1025x321Network(*builder, *container, DimsCHW{3, h, w}, weights, DataType::kFLOAT, log);
-    else if (model == "resnet18_2D") net = createResNet18_2D_513x257Network(*builder, *container, DimsCHW{3, h, w}, weights, DataType::kFLOAT, log);
+    else if (model == "resnet18_2D") net = createResNet18_2D_513x257Network(*builder, *container, DimsCHW{3, h, w}, weights, data_type, log);
     else { fprintf(stderr, "unknown model\n"); return 1; }
     if (argc > 8 && !strcmp(argv[8], "dump")) {
         // Host-only: write the plan of the network the reference's builder just described (no engine, no GPU) to <out.bin>.
-        const size_t n = redtail_serialize_network(net, 1, 0, nullptr, 0);
+        const size_t n = redtail_serialize_network(net, 1, fp16 ? 1 : 0, nullptr, 0);
         if (n == 0) { fprintf(stderr, "network is not serialisable\n"); return 5; }
         std::string blob(n, '\0');
-        redtail_serialize_network(net, 1, 0, &blob[0], n);
+        redtail_serialize_network(net, 1, fp16 ? 1 : 0, &blob[0], n);
         std::ofstream(argv[7], std::ios::binary).write(blob.data(), blob.size());
         printf("Network plan: %zu bytes, %d layers\n", n, net->getNbLayers());
         return 0;
     }
     builder->setMaxBatchSize(1);
     builder->setMaxWorkspaceSize(size_t(1) << 30);
+    builder->setHalf2Mode(fp16);
     ICudaEngine* engine = builder->buildCudaEngine(*net);
     net->destroy();
     builder->destroy();
@@ -125,13 +131,14 @@ int main(int argc, char** argv)
     cudaMemcpy(buf[ir], right.data(), right.size() * 4, cudaMemcpyHostToDevice);
     IExecutionContext* ctx = engine->createExecutionContext();
     Prof prof;
-    if (argc > 8 && !plan_mode) ctx->setProfiler(&prof);
+    const bool profile_mode = argc > 8 && !strcmp(argv[8], "profile");
+    if (profile_mode) ctx->setProfiler(&prof);
     const auto t0 = std::chrono::high_resolution_clock::now();
     const bool ok = ctx->execute(1, buf);
     const auto t1 = std::chrono::high_resolution_clock::now();
     if (!ok) { fprintf(stderr, "execute failed\n"); return 4; }
     printf("Host time: %.3f ms (%d engine steps)\n", std::chrono::duration<float, std::milli>(t1 - t0).count(), engine->getNbLayers());
-    if (argc > 8 && !plan_mode) printf("All layers: %.3f ms\n", prof.total);
+    if (profile_mode) printf("All layers: %.3f ms\n", prof.total);
     cudaMemcpy(out.data(), buf[io], out.size() * 4, cudaMemcpyDeviceToHost);
     std::ofstream(argv[7], std::ios::binary).write(reinterpret_cast<const char*>(out.data()), out.size() * 4);
     ctx->destroy();

@@ -12,6 +12,8 @@
 //     8  one accumulation chain for the whole run (no per-stage accumulator switch, no accumulator barriers)
 //    16  epilogue warps do not read TMEM (they only hand the buffer back)
 //    32  no tcgen05.fence::after_thread_sync in the MMA warp
+//    64  every A tile load reads a DIFFERENT 16 KB tile of a 256 MB tensor (L2/HBM traffic like the real kernel; B stays hot)
+//   128  B tiles are loaded once per CTA (weights resident): only A streams
 //
 // Build (no library dependencies):  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 \
 //        -I redtail_b200/csrc/kernels -I include tools/stagebench/stagebench.cu -o gpurun_out/stagebench
@@ -29,7 +31,7 @@ using namespace rt;
 constexpr int kThreads = 320;       // producer warp, MMA warp, 8 epilogue warps
 constexpr int kKC = 64;             // K elements per tile row (128 B, SWIZZLE_128B)
 
-struct Params { int n, rows, slots, stages, mode, nbuf; };
+struct Params { int n, rows, slots, stages, mode, nbuf, atiles; };
 
 __global__ void __launch_bounds__(kThreads, 1)
 stage_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Params p,
@@ -62,10 +64,11 @@ stage_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         for (int k = 0; k < loads; ++k) {
             if (!(p.mode & (1 | 2))) mbar_wait(&empty_bar[slot], phase ^ 1);
             uint8_t* st = smem + static_cast<size_t>(slot) * stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[slot], p.rows * (a_bytes + b_bytes));
+            mbar_arrive_expect_tx(&full_bar[slot], p.rows * (a_bytes + (((p.mode & 128) && k >= p.slots) ? 0 : b_bytes)));
             for (int r = 0; r < p.rows; ++r) {
-                tma_load_2d(st + r * a_bytes, &map_a, &full_bar[slot], 0, 0);
-                tma_load_2d(st + p.rows * a_bytes + r * b_bytes, &map_b, &full_bar[slot], 0, 0);
+                const int arow = (p.mode & 64) ? static_cast<int>(((static_cast<long long>(blockIdx.x) * p.stages + k) * p.rows + r) % p.atiles) * 128 : 0;
+                tma_load_2d(st + r * a_bytes, &map_a, &full_bar[slot], 0, arow);
+                if (!(p.mode & 128) || k < p.slots) tma_load_2d(st + p.rows * a_bytes + r * b_bytes, &map_b, &full_bar[slot], 0, 0);
             }
             if (++slot == p.slots) { slot = 0; phase ^= 1; }
         }
@@ -153,10 +156,11 @@ int main(int argc, char** argv) {
     const size_t smem = p.slots * stage_bytes + 1024 + 512;
     if (smem > 227 * 1024) { fprintf(stderr, "stage ring does not fit (%zu bytes)\n", smem); return 1; }
     __half *a, *b; long long* cyc;
-    cudaMalloc(&a, 128 * kKC * 2); cudaMalloc(&b, 256 * kKC * 2); cudaMalloc(&cyc, 16);
-    cudaMemset(a, 0, 128 * kKC * 2); cudaMemset(b, 0, 256 * kKC * 2); cudaMemset(cyc, 0, 16);
+    p.atiles = (p.mode & 64) ? 16384 : 1;
+    cudaMalloc(&a, static_cast<size_t>(p.atiles) * 128 * kKC * 2); cudaMalloc(&b, 256 * kKC * 2); cudaMalloc(&cyc, 16);
+    cudaMemset(a, 0, static_cast<size_t>(p.atiles) * 128 * kKC * 2); cudaMemset(b, 0, 256 * kKC * 2); cudaMemset(cyc, 0, 16);
     CUtensorMap ma, mb;
-    const uint64_t da[2] = {kKC, 128}, db[2] = {kKC, 256}, st[1] = {kKC * 2};
+    const uint64_t da[2] = {kKC, static_cast<uint64_t>(p.atiles) * 128}, db[2] = {kKC, 256}, st[1] = {kKC * 2};
     const uint32_t ba[2] = {kKC, 128}, bb[2] = {kKC, static_cast<uint32_t>(p.n)};
     if (make_tensor_map(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a, da, st, ba, nullptr, CU_TENSOR_MAP_SWIZZLE_128B) ||
         make_tensor_map(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b, db, st, bb, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) { fprintf(stderr, "tensor map failed\n"); return 2; }
