@@ -9,7 +9,7 @@
  * graph-capture + static-memory-plan executor whose every layer runs a hand-written sm_100a kernel through the
  * C-ABI of include/redtail_b200.h.  The following reference sources compile against it unchanged:
  * stereoDNN/sample_app/{nvsmall_1025x321,nvtiny_513x161,resnet18_1025x321,resnet18_2D_513x257}_net.cpp, networks.h,
- * sample_app/main.cpp and tests/tests_main.cpp (see INTEGRATION.md and tools/dropin_check.sh).
+ * sample_app/main.cpp and tests/tests_main.cpp (built by tools/dropin/build.sh, run by tests/test_gpu_dropin.py).
  *
  * This is an independent implementation of a published interface; nothing here is derived from TensorRT sources.
  */
@@ -18,6 +18,7 @@
 
 #include <cuda_runtime_api.h>
 
+#include <algorithm>   /* TensorRT's header pulls the standard algorithms in; sample_app/main.cpp:70 relies on it (std::find_if) */
 #include <cstddef>
 #include <cstdint>
 

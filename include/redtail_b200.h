@@ -22,6 +22,8 @@
  *                             the TensorRT-native layers the generated builders call
  *                             (sample_app/nvsmall_1025x321_net.cpp:36-53,350; resnet18_2D_513x257_net.cpp:613,722,766)
  *   rt_convert                CudaKernels::fp32Tofp16 / fp16Tofp32 lib/kernels.cu:340-375
+ *   rt_preprocess_bgr8 rt_disparity_to_u16 rt_write_png16
+ *                             the OpenCV image handling of the app around the engine (sample_app/main.cpp:83-98,317-330)
  *
  * There is no CPU fallback anywhere behind this header.
  */
@@ -58,6 +60,8 @@ enum { RT_LAYOUT_DENSE = 0, RT_LAYOUT_SPLIT16 = 1 };
 const char* rt_version(void);
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 uint64_t rt_launch_count(void);
+/* Adds n to that counter: the engine replays captured CUDA graphs, whose kernel launches do not pass through the library. */
+void rt_add_launch_count(uint64_t n);
 /* Name of the last kernel variant launched per op family, for tests that assert the tensor-core path ran. */
 const char* rt_last_kernel(void);
 
@@ -168,6 +172,17 @@ int  rt_conv2d_create(const rt_conv2d_desc* desc, rt_conv2d_plan** plan);
 void rt_conv2d_destroy(rt_conv2d_plan* plan);
 void rt_conv2d_out_dims(const rt_conv2d_plan* plan, int* out_h, int* out_w);
 int  rt_conv2d_enqueue(const rt_conv2d_plan* plan, int n, const void* x, void* y, void* stream);
+
+/* ---- image side of the apps (sample_app/main.cpp:83-98 readImgFile, :317-330 PNG output) -------------- */
+/* src: n 8-bit BGR images [src_h, src_w, 3] (row pitch src_pitch bytes, images src_pitch*src_h apart), device memory
+ * -> dst [n,3,dst_h,dst_w] fp32 RGB in [0,1]: float conversion, cv::resize INTER_AREA (down-scaling or identity only),
+ * BGR->RGB, HWC->CHW and the 1/255 scale in one kernel. */
+int rt_preprocess_bgr8(const void* src, int n, int src_h, int src_w, int64_t src_pitch, void* dst, int dst_h, int dst_w,
+                       void* stream);
+/* out[i] = saturate_u16(round(disp[i] * scale)): the 16-bit PNG payload (scale 256; 256*width for ResNet18_2D). */
+int rt_disparity_to_u16(const void* disp, void* out, int64_t count, float scale, void* stream);
+/* HOST: pixels [height,width] uint16 -> 16-bit greyscale PNG file (what cv::imwrite produces for a CV_16U Mat). */
+int rt_write_png16(const char* path, const uint16_t* pixels, int height, int width);
 
 #ifdef __cplusplus
 }

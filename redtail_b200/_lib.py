@@ -42,6 +42,10 @@ _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 KERNEL_API = {
     "rt_version": (C.c_char_p, []),
     "rt_launch_count": (C.c_uint64, []),
+    "rt_add_launch_count": (None, [C.c_uint64]),
+    "rt_preprocess_bgr8": (_I, [_P, _I, _I, _I, _L, _P, _I, _I, _P]),
+    "rt_disparity_to_u16": (_I, [_P, _P, _L, _F, _P]),
+    "rt_write_png16": (_I, [C.c_char_p, _P, _I, _I]),
     "rt_last_kernel": (C.c_char_p, []),
     "rt_cost_volume": (_I, [_I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rt_corr_cost_volume": (_I, [_I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

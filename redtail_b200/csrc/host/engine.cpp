@@ -395,6 +395,9 @@ struct TensorSlot {
     size_t elems = 0;          // per sample
     int binding = -1;          // >= 0: caller-owned buffer
     int alias_of = -1;         // shares storage with another tensor (shuffle)
+    int pair_of = -1;          // siamese partner: stored right behind tensor `pair_of` (at + batch * elems) so that one launch
+                               // of batch 2N covers both towers
+    bool has_partner = false;  // some tensor names this one as its pair_of: the allocation is twice the size
     size_t offset = 0;         // arena offset (bytes) when neither binding nor alias
     int first = -1, last = -1; // step liveness
     bool used = false;
@@ -405,6 +408,7 @@ struct ConvStep {
     rt_conv3d_desc desc{};
     rt_conv3d_plan* plan = nullptr;
     int in_id = -1, out_id = -1, skip_id = -1;
+    int batch_mul = 1;         // 2: the step also covers its siamese twin (same weights; inputs and outputs stored as pairs)
     std::string name;
     // CostVolume -> Conv3D pair replaced by the separable formulation (rt_costvol_conv3d_*): inputs are the two feature maps.
     bool cvfused = false;
@@ -434,6 +438,7 @@ public:
     explicit ContextImpl(EngineImpl* e);
     ~ContextImpl() override
     {
+        for (auto& g : graphs_) cudaGraphExecDestroy(g.exec);
         if (stream_) cudaStreamDestroy(stream_);
         if (arena_) cudaFree(arena_);
         if (workspace_) cudaFree(workspace_);
@@ -449,6 +454,14 @@ public:
 
 private:
     bool run(int batchSize, void** bindings, cudaStream_t stream, bool profile);
+    bool launch(int batchSize, void** bindings, cudaStream_t stream);
+    // One inference = ~25 kernel launches of 30-1000 us: the launch sequence of a (batch, bindings) pair is captured into a
+    // CUDA graph the second time it is seen and replayed afterwards (REDTAIL_ENGINE_GRAPH=0 keeps eager launches).
+    struct GraphEntry { int batch; std::vector<void*> bindings; cudaGraphExec_t exec; uint64_t launches; uint64_t stamp; };
+    std::vector<GraphEntry> graphs_;
+    std::vector<std::pair<int, std::vector<void*>>> seen_;    // keys executed eagerly once (capture happens on the second use)
+    bool graphs_enabled_ = true;
+    uint64_t stamp_ = 0;
     EngineImpl* engine_;
     cudaStream_t stream_ = nullptr;
     // Activations and scratch belong to the CONTEXT (as in TensorRT): several contexts of one engine may run concurrently
@@ -510,6 +523,7 @@ public:
     std::vector<TensorSlot> slots_;
     std::vector<int> bindings_;          // binding index -> tensor id
     std::vector<Step> steps_;
+    bool graph_safe_ = true;             // false when a step runs a plugin this library does not know (its enqueue() may synchronise)
     size_t arena_bytes_ = 0;             // per execution context
     size_t workspace_bytes_ = 0;         // per execution context
     std::vector<IPlugin*> configured_plugins_;
@@ -521,6 +535,7 @@ public:
 private:
     bool fail(const std::string& s) { logMsg(log_, ILogger::Severity::kERROR, s); return false; }
     bool assignLayoutsAndCreatePlans(bool fusion);
+    void pairSiameseSteps();
     bool planMemory();
 };
 
@@ -532,6 +547,66 @@ ContextImpl::ContextImpl(EngineImpl* e) : engine_(e)
     if (alloc_ok_ && e->arena_bytes_ > 0) alloc_ok_ = cudaMalloc(&arena_, e->arena_bytes_) == cudaSuccess;
     if (alloc_ok_ && e->workspace_bytes_ > 0) alloc_ok_ = cudaMalloc(&workspace_, e->workspace_bytes_) == cudaSuccess;
     if (!alloc_ok_) logMsg(e->log_, ILogger::Severity::kERROR, "createExecutionContext: cudaMalloc of the activation arena / workspace failed");
+    const char* g = getenv("REDTAIL_ENGINE_GRAPH");
+    graphs_enabled_ = !(g && g[0] == '0') && e->graph_safe_;
+}
+
+// Eager the first time a (batch, bindings) pair is seen (first-use work such as cudaFuncSetAttribute happens there),
+// captured into a graph the second time, replayed from then on.
+bool ContextImpl::launch(int batchSize, void** bindings, cudaStream_t stream)
+{
+    EngineImpl& e = *engine_;
+    if (!graphs_enabled_ || debug_sync_ || batchSize < 1 || batchSize > e.max_batch_ || bindings == nullptr)
+        return run(batchSize, bindings, stream, false);
+    std::vector<void*> key(bindings, bindings + e.getNbBindings());
+    for (auto& g : graphs_)
+        if (g.batch == batchSize && g.bindings == key) {
+            g.stamp = ++stamp_;
+            if (cudaGraphLaunch(g.exec, stream) != cudaSuccess) {
+                logMsg(e.log_, ILogger::Severity::kERROR, "enqueue: cudaGraphLaunch failed");
+                return false;
+            }
+            rt_add_launch_count(g.launches);
+            return true;
+        }
+    bool second = false;
+    for (auto& k : seen_) second = second || (k.first == batchSize && k.second == key);
+    if (!second) {
+        if (seen_.size() >= 16) seen_.erase(seen_.begin());
+        seen_.emplace_back(batchSize, key);
+        return run(batchSize, bindings, stream, false);
+    }
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)
+        return run(batchSize, bindings, stream, false);           // the caller is capturing already: just record into its graph
+    if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        (void)cudaGetLastError();
+        graphs_enabled_ = false;
+        return run(batchSize, bindings, stream, false);
+    }
+    const uint64_t l0 = rt_launch_count();
+    const bool ok = run(batchSize, bindings, stream, false);
+    const uint64_t captured = rt_launch_count() - l0;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (!ok || ce != cudaSuccess || graph == nullptr || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        graphs_enabled_ = false;                                  // e.g. a third-party plugin that synchronises in enqueue()
+        logMsg(e.log_, ILogger::Severity::kWARNING, "engine: CUDA graph capture of the step sequence failed, staying with eager launches");
+        return ok ? run(batchSize, bindings, stream, false) : false;
+    }
+    cudaGraphDestroy(graph);
+    if (graphs_.size() >= 8) {                                    // least recently used entry makes room
+        size_t lru = 0;
+        for (size_t i = 1; i < graphs_.size(); ++i) if (graphs_[i].stamp < graphs_[lru].stamp) lru = i;
+        cudaGraphExecDestroy(graphs_[lru].exec);
+        graphs_.erase(graphs_.begin() + lru);
+    }
+    graphs_.push_back(GraphEntry{batchSize, key, exec, captured, ++stamp_});
+    if (cudaGraphLaunch(exec, stream) != cudaSuccess) return false;
+    return true;                                                  // (the captured launches were counted while capturing)
 }
 
 // Weight helpers ---------------------------------------------------------------------------------------------------
@@ -651,7 +726,7 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                         st.out.push_back(out->id);
                         st.conv = cs;
                         st.run = [cs](int batch, const std::function<void*(int)>& ptr, void* ws, cudaStream_t s) {
-                            return rt_conv3d_enqueue(cs->plan, batch, ptr(cs->in_id), nullptr, ptr(cs->out_id), ws, s);
+                            return rt_conv3d_enqueue(cs->plan, batch * cs->batch_mul, ptr(cs->in_id), nullptr, ptr(cs->out_id), ws, s);
                         };
                         break;
                     }
@@ -681,6 +756,12 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
             case LKind::kScale: {
                 const float shift = weightScalar(d.shift, 0.f), scale = weightScalar(d.scale, 1.f), power = weightScalar(d.power, 1.f);
                 const int in_id = d.in[0]->id, out_id = d.out[0]->id;
+                // (x * 1 + 0)^1: the generator emits this identity in front of every tower (tensorrt_model_builder.py:134-136,
+                // nvsmall_1025x321_net.cpp:36-45).  No pass: the output is the input.
+                if (fusion && shift == 0.f && scale == 1.f && power == 1.f && slots_[out_id].binding < 0) {
+                    slots_[out_id].alias_of = in_id;
+                    continue;
+                }
                 const int64_t elems = static_cast<int64_t>(slots_[in_id].elems);
                 st.out.push_back(out_id);
                 st.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
@@ -798,7 +879,7 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                     st.out.push_back(out->id);
                     st.conv = cs;
                     st.run = [cs](int batch, const std::function<void*(int)>& ptr, void* ws, cudaStream_t s) {
-                        return rt_conv3d_enqueue(cs->plan, batch, ptr(cs->in_id), cs->skip_id >= 0 ? ptr(cs->skip_id) : nullptr,
+                        return rt_conv3d_enqueue(cs->plan, batch * cs->batch_mul, ptr(cs->in_id), cs->skip_id >= 0 ? ptr(cs->skip_id) : nullptr,
                                                  ptr(cs->out_id), ws, s);
                     };
                     break;
@@ -872,6 +953,7 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                     d.plugin->configure(ind.data(), static_cast<int>(ind.size()), outd.data(), static_cast<int>(outd.size()), max_batch_);
                 }
                 if (d.plugin->initialize() != 0) return fail(d.name + ": plugin initialize() failed");
+                if (op == nullptr) graph_safe_ = false;
                 configured_plugins_.push_back(d.plugin);
                 IPlugin* plugin = d.plugin;
                 std::vector<int> in_ids, out_ids;
@@ -921,6 +1003,7 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
         steps_.push_back(std::move(st));
     }
     if (!assignLayoutsAndCreatePlans(fusion)) return false;
+    if (fusion) pairSiameseSteps();
     if (!planMemory()) return false;
     plan_ = serializeNetwork(net, max_batch_, half2);
     return true;
@@ -1132,10 +1215,78 @@ bool EngineImpl::assignLayoutsAndCreatePlans(bool fusion)
     return true;
 }
 
+// Siamese towers: the generated builders emit the left and the right tower as two chains of layers with bit-identical
+// weights.  Two tensor-core conv steps that differ only in their tensors are run as ONE launch of
+// batch 2N: their inputs (and outputs) are stored as a pair -- the twin's tensor right behind the first one's N samples.
+void EngineImpl::pairSiameseSteps()
+{
+    if (const char* e = getenv("REDTAIL_ENGINE_SIAMESE")) if (e[0] == '0') return;
+    auto sameDesc = [](const rt_conv3d_desc& a, const rt_conv3d_desc& b) {
+        if (a.transposed != b.transposed || a.k != b.k || a.v != b.v || a.c != b.c || a.r != b.r || a.s != b.s) return false;
+        for (int i = 0; i < 3; ++i) if (a.stride[i] != b.stride[i] || a.pad[i] != b.pad[i]) return false;
+        for (int i = 0; i < 4; ++i) if (a.in_dims[i] != b.in_dims[i] || a.out_dims[i] != b.out_dims[i]) return false;
+        if (a.weights_dtype != b.weights_dtype || a.precision != b.precision || a.fuse_elu != b.fuse_elu ||
+            a.out_transposed != b.out_transposed || a.slice_d != b.slice_d || a.in_layout != b.in_layout ||
+            a.out_layout != b.out_layout || a.pad_end_d != b.pad_end_d || (a.bias == nullptr) != (b.bias == nullptr))
+            return false;
+        const size_t es = a.weights_dtype == RT_F16 ? 2 : 4;
+        const size_t wn = static_cast<size_t>(a.k) * a.v * a.c * a.r * a.s;
+        if (a.weights == nullptr || b.weights == nullptr || memcmp(a.weights, b.weights, wn * es) != 0) return false;
+        const size_t bn = a.transposed ? a.c : a.k;
+        return a.bias == nullptr || memcmp(a.bias, b.bias, bn * es) == 0;
+    };
+    auto resolved = [&](int id) { while (slots_[id].alias_of >= 0) id = slots_[id].alias_of; return id; };
+    auto pairable = [&](int a, int b) {        // may tensor b be stored behind tensor a?
+        if (a == b) return false;
+        const TensorSlot &x = slots_[a], &y = slots_[b];
+        if (y.pair_of == a) return true;                                   // already are
+        return x.binding < 0 && y.binding < 0 && x.pair_of < 0 && y.pair_of < 0 && !x.has_partner && !y.has_partner &&
+               x.elems == y.elems;
+    };
+    int paired = 0;
+    // The towers are emitted one after the other (all left layers, then all right layers), so the merged launch takes the
+    // position of the LATER twin, where both inputs exist.  Walking the first tower backwards keeps that legal: when layer i
+    // moves behind layer j, its consumer (layer i+1) has already moved behind layer j+1.
+    for (size_t ii = steps_.size(); ii-- > 0;) {
+        const size_t i = ii;
+        ConvStep* a = steps_[i].conv;
+        if (!a || a->cvfused || a->skip_id >= 0 || a->batch_mul != 1 || steps_[i].dropped || a->desc.precision == RT_PREC_SIMT) continue;
+        for (size_t j = i + 1; j < steps_.size(); ++j) {
+            ConvStep* b = steps_[j].conv;
+            if (!b || b->cvfused || b->skip_id >= 0 || b->batch_mul != 1 || steps_[j].dropped) continue;
+            if (!sameDesc(a->desc, b->desc)) continue;
+            const int ai = resolved(a->in_id), bi = resolved(b->in_id), ao = resolved(a->out_id), bo = resolved(b->out_id);
+            if (!pairable(ai, bi) || !pairable(ao, bo) || ai == bo || bi == ao) continue;
+            // a's output now appears at step j: nothing up to and including j may read it
+            bool legal = true;
+            for (size_t k = 0; k <= j && legal; ++k) {
+                if (steps_[k].dropped || k == i) continue;
+                for (int id : steps_[k].in) if (resolved(id) == ao) legal = false;
+            }
+            if (!legal) continue;
+            if (slots_[bi].pair_of < 0) { slots_[bi].pair_of = ai; slots_[ai].has_partner = true; }
+            if (slots_[bo].pair_of < 0) { slots_[bo].pair_of = ao; slots_[ao].has_partner = true; }
+            a->batch_mul = 2;
+            Step& sj = steps_[j];
+            sj.in.push_back(a->in_id);
+            sj.out.push_back(a->out_id);
+            sj.name = steps_[i].name + " || " + sj.name;
+            sj.run = steps_[i].run;                  // launches a's plan over [a's N samples | b's N samples]
+            sj.conv = a;
+            sj.workspace = rt_conv3d_workspace_size(a->plan, max_batch_ * 2);
+            steps_[i].dropped = true;
+            ++paired;
+            break;
+        }
+    }
+    steps_.erase(std::remove_if(steps_.begin(), steps_.end(), [](const Step& s) { return s.dropped; }), steps_.end());
+    if (paired) logMsg(log_, ILogger::Severity::kINFO, "engine: " + std::to_string(paired) + " siamese layer pairs run as one launch of twice the batch");
+}
+
 bool EngineImpl::planMemory()
 {
     auto root = [&](int id) {
-        while (slots_[id].alias_of >= 0) id = slots_[id].alias_of;
+        while (slots_[id].alias_of >= 0 || slots_[id].pair_of >= 0) id = slots_[id].alias_of >= 0 ? slots_[id].alias_of : slots_[id].pair_of;
         return id;
     };
     // Liveness over steps, on alias roots.
@@ -1157,8 +1308,10 @@ bool EngineImpl::planMemory()
     // First-fit over tensors sorted by size (descending); two tensors may overlap in memory iff their live ranges do not.
     std::vector<int> order;
     for (size_t i = 0; i < slots_.size(); ++i)
-        if (slots_[i].used && slots_[i].binding < 0 && slots_[i].alias_of < 0) order.push_back(static_cast<int>(i));
-    auto bytesOf = [&](int id) { return (slots_[id].elems * max_batch_ * sizeof(float) + 255) & ~static_cast<size_t>(255); };
+        if (slots_[i].used && slots_[i].binding < 0 && slots_[i].alias_of < 0 && slots_[i].pair_of < 0) order.push_back(static_cast<int>(i));
+    auto bytesOf = [&](int id) {
+        return (slots_[id].elems * max_batch_ * sizeof(float) * (slots_[id].has_partner ? 2 : 1) + 255) & ~static_cast<size_t>(255);
+    };
     std::sort(order.begin(), order.end(), [&](int a, int b) { return bytesOf(a) > bytesOf(b); });
     std::vector<int> placed;
     arena_bytes_ = 0;
@@ -1197,10 +1350,15 @@ bool ContextImpl::run(int batchSize, void** bindings, cudaStream_t stream, bool 
         return false;
     }
     std::function<void*(int)> ptr = [&](int id) -> void* {
-        while (e.slots_[id].alias_of >= 0) id = e.slots_[id].alias_of;
+        size_t extra = 0;
+        while (e.slots_[id].alias_of >= 0 || e.slots_[id].pair_of >= 0) {
+            if (e.slots_[id].alias_of >= 0) { id = e.slots_[id].alias_of; continue; }
+            extra += e.slots_[id].elems * static_cast<size_t>(batchSize) * sizeof(float);   // behind the partner's samples
+            id = e.slots_[id].pair_of;
+        }
         const TensorSlot& s = e.slots_[id];
-        if (s.binding >= 0) return bindings[s.binding];
-        return static_cast<char*>(arena_) + s.offset;
+        if (s.binding >= 0) return static_cast<char*>(bindings[s.binding]) + extra;
+        return static_cast<char*>(arena_) + s.offset + extra;
     };
     std::vector<cudaEvent_t> ev;
     if (profile) {
@@ -1240,7 +1398,7 @@ bool ContextImpl::execute(int batchSize, void** bindings)
         logMsg(engine_->log_, ILogger::Severity::kERROR, "execute: pending work on the default stream failed");
         return false;
     }
-    const bool ok = run(batchSize, bindings, stream_, profiler_ != nullptr);
+    const bool ok = profiler_ != nullptr ? run(batchSize, bindings, stream_, true) : launch(batchSize, bindings, stream_);
     const cudaError_t err = cudaStreamSynchronize(stream_);
     if (err != cudaSuccess) {
         logMsg(engine_->log_, ILogger::Severity::kERROR, std::string("execute: ") + cudaGetErrorString(err));
@@ -1251,7 +1409,7 @@ bool ContextImpl::execute(int batchSize, void** bindings)
 
 bool ContextImpl::enqueue(int batchSize, void** bindings, cudaStream_t stream, cudaEvent_t* inputConsumed)
 {
-    const bool ok = run(batchSize, bindings, stream, false);
+    const bool ok = launch(batchSize, bindings, stream);
     if (inputConsumed) cudaEventRecord(*inputConsumed, stream);
     return ok;
 }

@@ -167,6 +167,33 @@ __device__ __forceinline__ JobCoord decode_job(const TcParams& p, int job) {
     return j;
 }
 
+// All tcgen05.mma of one pipeline stage, fully unrolled (the issuing warp executes ~5 uniform-datapath instructions per
+// MMA and nothing else between them).  Measured on the round-1 kernel with ncu's warp-state sampling: the issuing warp
+// spent 75 % of its time in its own scalar control code -- 125 instructions per stage plus 63 per filter row at ~6 clk each
+// for a lone warp -- while the tensor pipe was 48 % active; the "fixed ~1.1 k clk per stage" of round 1 was this code, not
+// a hardware hand-off cost.  nr (1..3 filter rows in this stage) is the only run-time quantity left.
+template <int KC16, int MT, bool SPLIT, int COUT_PAD, int ACC_COLS>
+__device__ __forceinline__ void umma_issue_stage(int nr, uint32_t lo_a, uint32_t lo_l, uint32_t lo_b, uint32_t grp_a16,
+                                                 uint32_t grp_b16, uint32_t tile_a16, uint64_t desc_hi, uint64_t desc_b_hi,
+                                                 uint32_t idesc_full, uint32_t idesc_half, uint32_t d0, uint32_t acc_first, uint32_t acc_first_lo) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (i < nr) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t xa = lo_a + i * grp_a16 + mt * tile_a16, xl = lo_l + i * grp_a16 + mt * tile_a16;
+                const uint32_t xb = lo_b + i * grp_b16;
+                const uint32_t dt = d0 + mt * ACC_COLS;
+#pragma unroll
+                for (int kk = 0; kk < KC16; ++kk) {          // +32 bytes = one K=16 slice inside the swizzle atom
+                    umma_f16(dt, desc_hi | (xa + 2 * kk), desc_b_hi | (xb + 2 * kk), idesc_full, (i == 0 && kk == 0) ? acc_first : 1u);
+                    if (SPLIT) umma_f16(dt + COUT_PAD, desc_hi | (xl + 2 * kk), desc_b_hi | (xb + 2 * kk), idesc_half, (i == 0 && kk == 0) ? acc_first_lo : 1u);
+                }
+            }
+        }
+    }
+}
+
 // Epilogue register budget: each of the 8 epilogue warps owns one TMEM lane quarter (warp_id % 4) and one half of the
 // output channels, i.e. CPH = cout_pad / 2 columns of D0 (and of D1 in split mode) per thread.
 template <int CPH, bool SPLIT, int MT>
@@ -268,6 +295,56 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             uint32_t phase = 0;
             int buf = 0;
             uint32_t bphase = 0;
+            if (chunk_rows >= gr) {
+                // ---- fast path: a chunk is `chunk_kb` whole stages (every layer of the nets; sub-stage chunks below) ----
+                uint32_t st_lo = (ring_addr >> 4) | (1u << 16);                  // descriptor low word of the current slot
+                const uint32_t st_lo0 = st_lo, stage16 = stage_bytes >> 4, a16 = a_bytes >> 4;
+                for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
+                    int cls = 0;
+                    {
+                        const int r = job % p.jobs_per_sample;
+                        while (cls + 1 < p.nclasses && r >= p.cls[cls + 1].job_begin) ++cls;
+                    }
+                    const int nkb = p.cls[cls].ntaps * ncb;
+                    unsigned long long nrp = p.cls[cls].nr_pack;
+                    int cb_left = 0, nr = 1, kb_in_chunk = 0;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        if (cb_left == 0) {
+                            nr = gr == 1 ? 1 : static_cast<int>(nrp & 3ull);
+                            nrp >>= 2;
+                            cb_left = ncb;
+                        }
+                        --cb_left;
+                        const bool first = kb_in_chunk == 0;
+                        if (first) mbar_wait(&tmem_empty[buf], bphase ^ 1);      // epilogue drained this buffer
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const bool close = (++kb_in_chunk == chunk_kb) || (kb == nkb - 1);
+                        if (elect_one_sync()) {
+                            const uint32_t d0 = tmem_base + static_cast<uint32_t>(buf * kBufCols);
+                            const uint32_t lo_l = st_lo + a16, lo_b = st_lo + (SPLIT ? 2u : 1u) * a16;
+                            const uint32_t acc_first = first ? 0u : 1u;
+                            // D1 is initialised by the first MMA (N covers D0|D1) when the weight tile carries W_lo rows; without them
+                            // (fp16-exact weights) the A_lo x W_hi product is the first to touch D1 and must overwrite it
+                            const uint32_t acc_first_lo = p.wlo ? 1u : acc_first;
+                            if (kc16 == 4)
+                                umma_issue_stage<4, MT, SPLIT, kCoutPad, kAccCols>(nr, st_lo, lo_l, lo_b, grp_a16, grp_b16, tile_a16, desc_hi, desc_b_hi, idesc_full, idesc_half, d0, acc_first, acc_first_lo);
+                            else if (kc16 == 2)
+                                umma_issue_stage<2, MT, SPLIT, kCoutPad, kAccCols>(nr, st_lo, lo_l, lo_b, grp_a16, grp_b16, tile_a16, desc_hi, desc_b_hi, idesc_full, idesc_half, d0, acc_first, acc_first_lo);
+                            else
+                                umma_issue_stage<1, MT, SPLIT, kCoutPad, kAccCols>(nr, st_lo, lo_l, lo_b, grp_a16, grp_b16, tile_a16, desc_hi, desc_b_hi, idesc_full, idesc_half, d0, acc_first, acc_first_lo);
+                            umma_commit(&empty_bar[stage]);                      // slot free once these MMAs retire
+                            if (close) umma_commit(&tmem_full[buf]);             // chunk complete
+                        }
+                        __syncwarp();
+                        if (close) {
+                            kb_in_chunk = 0;
+                            if (++buf == kNumBuf) { buf = 0; bphase ^= 1; }
+                        }
+                        if (++stage == stages) { stage = 0; phase ^= 1; st_lo = st_lo0; } else st_lo += stage16;
+                    }
+                }
+            } else
             for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
                 const JobCoord jc = decode_job(p, job);
                 const int nkb = p.cls[jc.cls].ntaps * ncb;
@@ -314,7 +391,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                                     const uint32_t dt = d0 + mt * kAccCols;
                                     for (int kk = 0; kk < kc16; ++kk) {
                                         umma_f16(dt, desc_hi | xa, desc_b_hi | xb, idesc_full, (open || i > i0 || kk > 0) ? 1u : 0u);
-                                        if (SPLIT) umma_f16(dt + kCoutPad, desc_hi | xl, desc_b_hi | xb, idesc_half, 1u);
+                                        if (SPLIT) umma_f16(dt + kCoutPad, desc_hi | xl, desc_b_hi | xb, idesc_half, (p.wlo || open || i > i0 || kk > 0) ? 1u : 0u);
                                         xa += 2; xl += 2; xb += 2;             // +32 bytes = one K=16 slice inside the swizzle atom
                                     }
                                 }
@@ -585,6 +662,10 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     p.split = split;
     p.wlo = wlo ? 1 : 0;
     p.kc = cin >= 64 ? 64 : cin;
+    if (const char* e = getenv("REDTAIL_TC_KC")) {           // experiment switch: narrower K blocks = smaller, more numerous stages
+        const int kc = atoi(e);
+        if ((kc == 16 || kc == 32 || kc == 64) && kc <= p.kc && cin % kc == 0) p.kc = kc;
+    }
     p.ncb = cin / p.kc;
     p.cout = cout; p.cout_pad = cout_pad; p.nb = nb;
     p.fuse_elu = d.fuse_elu;

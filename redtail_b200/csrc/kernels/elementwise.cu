@@ -172,6 +172,7 @@ extern "C" {
 const char* rt_version(void) { return "redtail_b200 0.1 (sm_100a)"; }
 uint64_t rt_launch_count(void) { return g_launches.load(); }
 const char* rt_last_kernel(void) { return g_last_kernel; }
+void rt_add_launch_count(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int rt_elu(int dtype, const void* x, void* y, int64_t count, void* stream) {
     return dispatch_unary<kElu>(dtype, x, y, count, UnaryArgs{0, 1, 1}, stream, "elu");

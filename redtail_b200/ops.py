@@ -365,3 +365,31 @@ def launch_count():
 
 def last_kernel():
     return kernels_lib().rt_last_kernel().decode()
+
+
+def preprocess_bgr8(images, out_h, out_w):
+    """uint8 [N,H,W,3] BGR (what cv::imread returns) on the device -> float32 [N,3,out_h,out_w] RGB in [0,1]:
+    readImgFile of sample_app/main.cpp:83-98 (float, INTER_AREA resize, BGR->RGB, CHW, /255) as one kernel."""
+    _dev(images)
+    assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[3] == 3 and images.is_contiguous()
+    n, h, w, _ = images.shape
+    out = torch.empty((n, 3, out_h, out_w), dtype=torch.float32, device=images.device)
+    _check(kernels_lib().rt_preprocess_bgr8(_p(images), n, h, w, 3 * w, _p(out), out_h, out_w, _stream()), "rt_preprocess_bgr8")
+    return out
+
+
+def disparity_to_u16(disp, scale=256.0):
+    """float32 disparity -> uint16 payload of the KITTI-style PNG (sample_app/main.cpp:317-330)."""
+    _dev(disp)
+    assert disp.dtype == torch.float32 and disp.is_contiguous()
+    out = torch.empty(disp.shape, dtype=torch.uint16, device=disp.device)
+    _check(kernels_lib().rt_disparity_to_u16(_p(disp), _p(out), disp.numel(), float(scale), _stream()), "rt_disparity_to_u16")
+    return out
+
+
+def write_png16(path, pixels):
+    """HOST: numpy uint16 [H,W] -> 16-bit greyscale PNG."""
+    import numpy as np
+    a = np.ascontiguousarray(pixels, dtype=np.uint16)
+    assert a.ndim == 2
+    _check(kernels_lib().rt_write_png16(str(path).encode(), a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1]), "rt_write_png16")

@@ -87,3 +87,59 @@ def test_reference_builder_plan_roundtrip(tmp_path):
             assert "engine rebuilt from it" in p.stdout
         outs.append(np.fromfile(out, dtype=np.float32))
     assert np.array_equal(outs[0], outs[1])
+
+
+def _write_png8(path, chw01):
+    """[3,h,w] float in [0,1] (RGB) -> 8-bit RGB PNG (stdlib zlib; the app reads it with cv::imread)."""
+    import struct
+    import zlib
+    img = np.clip(np.rint(chw01 * 255.0), 0, 255).astype(np.uint8).transpose(1, 2, 0)
+    h, w, _ = img.shape
+    raw = b"".join(b"\x00" + img[y].tobytes() for y in range(h))
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) +
+                chunk(b"IDAT", zlib.compress(raw, 3)) + chunk(b"IEND", b""))
+    return img
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16"])
+def test_reference_sample_app_unchanged(tmp_path, mode):
+    """stereoDNN/sample_app/main.cpp compiled UNCHANGED (tools/dropin/build.sh -> nvstereo_sample_app): PNG images in
+    (cv::imread / resize / cvtColor through the cv:: stand-in), the reference's NVTiny builder, this engine, raw disparity +
+    16-bit PNG out (main.cpp:83-98,176-330).  The disparity must equal what the Python binding computes from the same
+    8-bit images, and the PNG must hold round(256 * disparity)."""
+    exe = _need("nvstereo_sample_app")
+    import torch
+    from redtail_b200 import StereoEngine
+    h, w = 161, 513
+    l, r = oio.load_sample_pair()
+    l, r = oio.resize_pair(l, r, h, w)
+    l8 = _write_png8(tmp_path / "l.png", l)
+    r8 = _write_png8(tmp_path / "r.png", r)
+    wpath = oio.weights_path("nvtiny")
+    if mode == "fp16":
+        wpath = oio.write_fp16_weights(wpath, str(tmp_path / "w16.bin"))
+    out = tmp_path / "disp.bin"
+    p = subprocess.run([exe, "nvsmall", str(w), str(h), wpath, str(tmp_path / "l.png"), str(tmp_path / "r.png"), str(out), mode],
+                       capture_output=True, text=True, timeout=600)
+    print(p.stdout[-1500:], p.stderr[-1500:])
+    assert p.returncode == 0
+    disp = np.fromfile(out, dtype=np.float32).reshape(h, w)
+    # the same pre-processing in numpy: identity resize, RGB, CHW, * float(1/255)
+    inv = np.float32(1.0 / 255.0)
+    lt = torch.from_numpy(np.ascontiguousarray(l8.transpose(2, 0, 1)).astype(np.float32) * inv)[None].cuda()
+    rt = torch.from_numpy(np.ascontiguousarray(r8.transpose(2, 0, 1)).astype(np.float32) * inv)[None].cuda()
+    eng = StereoEngine("nvtiny", h, w, wpath, weights_dtype=mode)
+    ref = eng(lt, rt).cpu().numpy()[0]
+    assert np.abs(disp - ref).max() <= 1e-5
+    # 16-bit PNG written by the app (cv::imwrite of the CV_16U Mat)
+    try:
+        import cv2
+    except ImportError:
+        return
+    png = cv2.imread(str(out) + ".png", cv2.IMREAD_UNCHANGED)
+    assert png is not None and png.dtype == np.uint16 and png.shape == (h, w)
+    assert np.abs(png.astype(np.int32) - np.clip(np.rint(disp * np.float32(256)), 0, 65535).astype(np.int32)).max() <= 0

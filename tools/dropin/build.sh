@@ -23,4 +23,8 @@ $CXX -o "$OUT/nvstereo_tests" "$OUT/tests_main.o" "$OUT/gtest_lite.o" $LIB
 # sample_app/main.cpp does and runs the engine on raw .bin images.
 $CXX $INC -I"$REF/sample_app" -c "$ROOT/tools/dropin/net_driver.cpp" -o "$OUT/net_driver.o"
 $CXX -o "$OUT/nvstereo_net_driver" "$OUT/net_driver.o" "$OUT"/*_net.o $LIB
-echo "built: $OUT/nvstereo_tests $OUT/nvstereo_net_driver"
+# The reference's sample application itself, UNCHANGED (sample_app/main.cpp: PNG in, engine, binary + 16-bit PNG out),
+# against the cv:: stand-in of tools/dropin/include/opencv2 (OpenCV's C++ headers are not in this image).
+$CXX $INC -I"$REF/sample_app" -c "$REF/sample_app/main.cpp" -o "$OUT/main.o"
+$CXX -o "$OUT/nvstereo_sample_app" "$OUT/main.o" "$OUT"/*_net.o $LIB -lz
+echo "built: $OUT/nvstereo_tests $OUT/nvstereo_net_driver $OUT/nvstereo_sample_app"

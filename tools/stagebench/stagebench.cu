@@ -14,6 +14,7 @@
 //    32  no tcgen05.fence::after_thread_sync in the MMA warp
 //    64  every A tile load reads a DIFFERENT 16 KB tile of a 256 MB tensor (L2/HBM traffic like the real kernel; B stays hot)
 //   128  B tiles are loaded once per CTA (weights resident): only A streams
+//   256  the MMA warp issues no MMAs (TMA / hand-off cost alone)
 //
 // Build (no library dependencies):  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 \
 //        -I redtail_b200/csrc/kernels -I include tools/stagebench/stagebench.cu -o gpurun_out/stagebench
@@ -72,6 +73,15 @@ stage_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             }
             if (++slot == p.slots) { slot = 0; phase ^= 1; }
         }
+        if (p.mode & 2) {
+            // free-running producer: nobody consumed the full barriers, so wait here until the last load of every slot has
+            // landed (a CTA must not exit with bulk copies in flight)
+            for (int s = 0; s < p.slots && s < loads; ++s) {
+                const int n_s = (loads - s + p.slots - 1) / p.slots;
+                mbar_wait(&full_bar[s], static_cast<uint32_t>((n_s - 1) & 1));
+            }
+            __nanosleep(4000);
+        }
     } else if (warp == 1) {
         // ---- MMA issuer ----
         const uint32_t idesc = umma_idesc_f16(128, p.n);
@@ -94,7 +104,7 @@ stage_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                 for (int r = 0; r < p.rows; ++r) {
                     uint32_t xa = ((st + r * a_bytes) >> 4) | (1u << 16);
                     uint32_t xb = ((st + p.rows * a_bytes + r * b_bytes) >> 4) | (1u << 16);
-                    for (int kk = 0; kk < kKC / 16; ++kk) {
+                    for (int kk = 0; kk < kKC / 16 && !(p.mode & 256); ++kk) {
                         const uint32_t acc = (p.mode & 8) ? (k > 0 || r > 0 || kk > 0) : (r > 0 || kk > 0);
                         umma_f16(d, desc_hi | xa, desc_hi | xb, idesc, acc ? 1u : 0u);
                         xa += 2; xb += 2;
@@ -108,8 +118,8 @@ stage_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             if (++slot == p.slots) { slot = 0; phase ^= 1; }
             if (!(p.mode & 8)) { if (++buf == p.nbuf) { buf = 0; bphase ^= 1; } }
         }
-    } else {
-        // ---- epilogue ----
+    } else if (warp >= 2) {
+        // ---- epilogue (whole warps only: tcgen05.ld is .sync.aligned) ----
         const int q = warp & 3, half = (warp - 2) >> 2;
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         float sink = 0.f;
