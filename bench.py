@@ -200,16 +200,165 @@ def run_reference_arm(args):
     }))
 
 
+# BASELINE.json configs beyond the headline one (configs[1] = NVSmall fp32 batch 1, the default of this script).  The ResNet
+# networks run from plans written host-only by the reference's own generated builders (tools/dropin/build.sh -> dropin/_ref/plans).
+OTHER_CONFIGS = {
+    # C3: "ResNet18-2D 1025x321 fp16 batch=32 on 1 B200 (fast 2D-correlation variant)"
+    "resnet18_2d": dict(plan="resnet18_2D_1025x321_fp16.plan", batch=32, what="ResNet18-2D 1025x321 fp16 weights",
+                        golden="disp_resnet18_2D_1025x321_fp16w_f64oracle.npy", px_scale=1025.0, tol=1e-2,
+                        gflop_per_pair=65.2, stack_prefix=("conv2D_", "deconv2D_", "left_", "right_")),
+    # C4: "ResNet18 full-3D 1025x321 fp16 batch=64 sharded across 8xB200" -> 8 pairs per GPU
+    "resnet18": dict(plan="resnet18_1025x321_fp16.plan", batch=8, what="ResNet-18 full-3D 1025x321 fp16 weights",
+                     golden="disp_resnet18_1025x321_fp16w_f64oracle.npy", px_scale=1.0, tol=1e-2,
+                     gflop_per_pair=1506.3, stack_prefix=("conv3D_", "deconv3D_")),
+    # the fp16 weight file of the headline net (trt_weights_fp16.bin)
+    "nvsmall_fp16": dict(plan=None, batch=1, what="NVSmall 1025x321 fp16 weights",
+                         golden="disp_nvsmall_1025x321_fp16w_f64oracle.npy", px_scale=1.0, tol=1e-2,
+                         gflop_per_pair=726.0, stack_prefix=("conv3D_", "deconv3D_")),
+}
+
+
+def run_other_config(args):
+    """bench.py --config resnet18_2d | resnet18 | nvsmall_fp16: same timing contract as the headline run (device-resident
+    `value`, host-buffer `e2e`, max over ranks), fewer extras."""
+    import torch
+    import torch.distributed as dist
+    cfg = OTHER_CONFIGS[args.config]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH,ENV")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from redtail_b200 import StereoEngine, ops
+    from redtail_b200.parallel import OverlappedGather
+    from redtail_b200.weights import write_fp16_weight_file
+    golden_dir = os.path.join(ROOT, "tests", "golden")
+    B = args.batch if args.batch_given else cfg["batch"]
+    if cfg["plan"] is None:
+        import tempfile
+        wpath = write_fp16_weight_file(WEIGHTS, os.path.join(tempfile.gettempdir(), "bench_nvsmall_fp16_%d.bin" % rank))
+        eng = StereoEngine("nvsmall", H, W, wpath, max_batch=B, weights_dtype="fp16")
+    else:
+        ppath = os.path.join(ROOT, "dropin", "_ref", "plans", cfg["plan"])
+        if not os.path.exists(ppath):
+            raise SystemExit("bench.py: %s not found -- run tools/dropin/build.sh where the reference checkout exists" % ppath)
+        with open(ppath, "rb") as f:
+            eng = StereoEngine.deserialize(f.read(), max_batch=B)
+    left_np, right_np = synthetic_pairs(B, seed=1234 + 100 * rank)
+    h_left, h_right = torch.from_numpy(left_np).pin_memory(), torch.from_numpy(right_np).pin_memory()
+    h_disp = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+    d_left, d_right = h_left.cuda(), h_right.cuda()
+    d_disp = torch.empty((B, H, W), dtype=torch.float32, device="cuda")
+    og = OverlappedGather((B, H, W), torch.float32, torch.device("cuda", local)) if world > 1 else None
+
+    def step_device():
+        if og is None:
+            eng(d_left, d_right, out=d_disp)
+        else:
+            eng(d_left, d_right, out=og.next_buffer())
+            og.submit()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    if og is not None:
+        og.flush()
+    e1.record()
+    barrier()
+    launches = ops.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    for _ in range(2):
+        eng.execute_host(h_left, h_right, h_disp)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.execute_host(h_left, h_right, h_disp)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join()
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # parity of this configuration: the reference's sample pair against the float64 oracle run with the same fp16 weights
+    l = np.load(os.path.join(golden_dir, "images", "kitti_left_1025x321.f16.npy")).astype(np.float32)
+    r = np.load(os.path.join(golden_dir, "images", "kitti_right_1025x321.f16.npy")).astype(np.float32)
+    lt = torch.from_numpy(np.repeat(l[None], B, 0)).cuda()
+    rt = torch.from_numpy(np.repeat(r[None], B, 0)).cuda()
+    d = eng(lt, rt).cpu().numpy()
+    gold = np.load(os.path.join(golden_dir, cfg["golden"]))
+    err = np.abs(d[0].astype(np.float64) - gold) * cfg["px_scale"]
+    same = float(np.abs(d - d[0:1]).max()) * cfg["px_scale"]
+    disparity_l1 = {"max": float(err.max()), "mean": float(err.mean()), "unit": "px", "tolerance": cfg["tol"], "pass": bool(err.max() <= cfg["tol"]),
+                    "vs": "float64 CPU oracle with the fp16 weights (graph of the reference's generated builder) on the reference's sample pair",
+                    "max_diff_between_batch_items": same}
+    peaks = measured_peaks()
+    acc = {}
+    for name, t_ms in eng.profile(d_left, d_right):
+        acc[name] = acc.get(name, 0.0) + t_ms
+    stack_ms = sum(t for n, t in acc.items() if n.startswith(cfg["stack_prefix"]))
+    tf = cfg["gflop_per_pair"] * B / stack_ms / 1e3 if stack_ms > 0 else 0.0
+    pairs = world * B * args.steps
+    value = pairs / (ms * 1e-3)
+    print(json.dumps({
+        "metric": "stereo pairs/sec %s" % cfg["what"], "value": value, "unit": "stereo pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 activations (fp16-split tensor-core products), fp16 weights", "data": "synthetic",
+        "config": {"workload": "%s, batch=%d per GPU (BASELINE config %s)" % (cfg["what"], B, args.config), "pairs_per_step": world * B,
+                   "parallelism": "dp%d (independent pairs, NCCL all-gather of disparity maps)" % world,
+                   "l2": "per-step working set >> 126 MB L2; no explicit flush"},
+        "e2e": {"value": pairs / e2e_s, "unit": "stereo pairs/s", "h2d_bytes_per_step": int(2 * B * 3 * H * W * 4), "d2h_bytes_per_step": int(B * H * W * 4)},
+        "gpu_launches": int(launches), "disparity_l1": disparity_l1, "clocks": sampler.summary(),
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["tflops_sustained"],
+                     "traffic": None, "kernel": "conv / transposed-conv layers of the net (%s*), algorithmic %.1f GFLOP/pair" % ("|".join(cfg["stack_prefix"]), cfg["gflop_per_pair"]),
+                     "peak_source": peaks["source"] + " cuBLAS bf16 (sustained)", "share_of_step": stack_ms / sum(acc.values()) if acc else None},
+        "layer_ms": {k: round(v, 4) for k, v in acc.items()},
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=1, help="stereo pairs per GPU per step (BASELINE config: 1)")
+    ap.add_argument("--batch", type=int, default=None, help="stereo pairs per GPU per step (default: the BASELINE config's: 1 for nvsmall)")
+    ap.add_argument("--config", default="nvsmall", choices=["nvsmall"] + sorted(OTHER_CONFIGS),
+                    help="nvsmall = BASELINE configs[1] (the headline metric); the others are the remaining GPU configs of BASELINE.json")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.batch_given = args.batch is not None
+    if args.batch is None:
+        args.batch = 1
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "ours" and args.config != "nvsmall":
+        run_other_config(args)
+        return
 
     if args.impl == "reference":
         run_reference_arm(args)
@@ -314,9 +463,24 @@ def main():
         eng(d_left, d_right, out=d_disp)
         torch.cuda.synchronize()
         err = np.abs(d_disp[0].cpu().numpy().astype(np.float64) - np.load(gpath).astype(np.float64))
-        disparity_l1 = {"max": float(err.max()), "mean": float(err.mean()), "unit": "px", "tolerance": 1e-3,
-                        "pass": bool(err.max() <= 1e-3),
+        disparity_l1 = {"max": float(err.max()), "mean": float(err.mean()), "p99.99": float(np.quantile(err, 0.9999)), "unit": "px",
+                        "tolerance": 1e-3, "pass": bool(err.max() <= 1e-3), "pixels_over_tolerance": int((err > 1e-3).sum()),
                         "vs": "float64 CPU oracle (fixture-pinned ops, reference's weights) on the timed synthetic pair, seed 1234"}
+        # How far plain fp32 arithmetic is from float64 on this very input: the same graph on the exact-fp32 CUDA-core kernels
+        # (REDTAIL_CONV3D_PRECISION=simt, no tensor cores).  Pixels at the synthetic depth discontinuity have a bimodal
+        # soft-argmin whose value moves by millipixels with the last bits of the cost volume, so ANY fp32 build (the reference's
+        # TensorRT FP32 engine included) differs from float64 there by more than 1e-3; the tensor-core path is reported next to it.
+        os.environ["REDTAIL_CONV3D_PRECISION"] = "simt"
+        try:
+            eng32 = StereoEngine("nvsmall", H, W, WEIGHTS, max_batch=1)
+        finally:
+            del os.environ["REDTAIL_CONV3D_PRECISION"]
+        d32 = eng32(d_left[:1], d_right[:1])
+        torch.cuda.synchronize()
+        e32 = np.abs(d32[0].cpu().numpy().astype(np.float64) - np.load(gpath).astype(np.float64))
+        disparity_l1["fp32_cuda_core_path"] = {"max": float(e32.max()), "mean": float(e32.mean()), "pixels_over_tolerance": int((e32 > 1e-3).sum())}
+        disparity_l1["no_worse_than_fp32_arithmetic"] = bool(err.max() <= e32.max() and (err > 1e-3).sum() <= (e32 > 1e-3).sum())
+        del eng32, d32
 
     # ---- per-kernel roofline numbers: CUDA events around every engine step, on the engine's stream ----
     peaks = measured_peaks()

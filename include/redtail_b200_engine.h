@@ -32,6 +32,12 @@ void rt_stereo_destroy(rt_stereo_engine* engine);
 int rt_stereo_enqueue(rt_stereo_engine* engine, int batch, const float* left, const float* right, float* disp, void* stream);
 /* Host buffers (pinned for full speed): H2D copies, inference and the D2H copy, synchronous. */
 int rt_stereo_execute_host(rt_stereo_engine* engine, int batch, const float* left, const float* right, float* disp);
+/* The app's whole loop body (sample_app/main.cpp:83-98,287-330) with the image handling on the GPU: host 8-bit BGR images
+ * [batch, src_h, src_w, 3] as cv::imread returns them (src >= network size) -> H2D of the 8-bit data, rt_preprocess_bgr8
+ * (float, INTER_AREA resize, BGR->RGB, CHW, /255), inference, D2H of the disparity (disp, may be NULL) and/or of its
+ * KITTI-style 16-bit payload round(disp * u16_scale) (disp_u16, may be NULL; rt_write_png16 writes it).  Synchronous. */
+int rt_stereo_execute_images(rt_stereo_engine* engine, int batch, const uint8_t* left_bgr, const uint8_t* right_bgr,
+                             int src_h, int src_w, float* disp, uint16_t* disp_u16, float u16_scale);
 /* Runs once with per-layer CUDA-event timing (IProfiler) and writes "layer name\tms\n" lines into buf. */
 int rt_stereo_profile(rt_stereo_engine* engine, int batch, const float* left, const float* right, float* disp,
                       char* buf, size_t buf_len);
@@ -41,6 +47,11 @@ int rt_stereo_profile(rt_stereo_engine* engine, int batch, const float* left, co
  * size (0 on error); rt_stereo_deserialize rebuilds an engine from it (no weight file needed). */
 size_t rt_stereo_serialize(const rt_stereo_engine* engine, void* buf, size_t buf_len);
 int rt_stereo_deserialize(const void* plan, size_t plan_size, rt_stereo_engine** engine);
+/* Same, with the plan's maximum batch size replaced by max_batch (> 0): a plan is a network description, so the batch it
+ * was dumped with is not binding.  This is how the reference's other networks (ResNet-18, ResNet18_2D: plans written by
+ * the reference's own generated builders through ICudaEngine::serialize or tools/dropin's host-only dump) are run at the
+ * batch sizes of BASELINE.json's configs. */
+int rt_stereo_deserialize_batch(const void* plan, size_t plan_size, int max_batch, rt_stereo_engine** engine);
 /* Introspection. */
 int rt_stereo_num_layers(const rt_stereo_engine* engine);
 size_t rt_stereo_device_bytes(const rt_stereo_engine* engine);

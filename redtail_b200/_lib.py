@@ -87,6 +87,8 @@ ENGINE_API = {
     "rt_stereo_profile": (_I, [_P, _I, _P, _P, _P, C.c_char_p, C.c_size_t]),
     "rt_stereo_serialize": (C.c_size_t, [_P, _P, C.c_size_t]),
     "rt_stereo_deserialize": (_I, [_P, C.c_size_t, C.POINTER(_P)]),
+    "rt_stereo_deserialize_batch": (_I, [_P, C.c_size_t, _I, C.POINTER(_P)]),
+    "rt_stereo_execute_images": (_I, [_P, _I, _P, _P, _I, _I, _P, _P, _F]),
     "rt_stereo_num_layers": (_I, [_P]),
     "rt_stereo_device_bytes": (C.c_size_t, [_P]),
     "rt_stereo_last_error": (C.c_char_p, []),

@@ -694,53 +694,65 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                 cd.weights_dtype = rtType(d.kw.type); cd.weights = d.kw.values;
                 cd.bias = d.bw.count > 0 ? d.bw.values : nullptr;
                 TensorImpl* out = d.out[0];
-                const int nxt = fusion ? soleConsumer(out) : -1;
+                int nxt = fusion ? soleConsumer(out) : -1;
+                // A 2-D (transposed) convolution is a 3-D one with V = D = 1 ([K,1,H,W] == [K,H,W]): the tower convs, the
+                // ResNet18_2D encoder / decoder and its deconvolutions run on the same tcgen05 implicit-GEMM kernel as the 3-D
+                // stack, with its epilogue fusions (+skip, ELU).  Channel counts that are not a K-block multiple (the 33-channel
+                // concat of ResNet18_2D) are zero-padded by the kernel's re-layout pass.  Only the 5x5 first layer stays on the
+                // CUDA-core kernel (filter larger than 3x3).
+                const char* pe2 = getenv("REDTAIL_CONV3D_PRECISION");
+                const bool simt_only = (pe2 && !strcmp(pe2, "simt")) || getenv("REDTAIL_SIMT_TOWERS") != nullptr;
+                const bool tr2 = d.kind == LKind::kDeconv;
+                const int ho2 = out->dims.d[1], wo2 = out->dims.d[2];
+                rt_conv3d_desc c3{};
+                c3.transposed = tr2 ? 1 : 0;
+                if (!tr2) { c3.k = cd.cout; c3.c = cd.cin; } else { c3.k = cd.cin; c3.c = cd.cout; }   // deconv weights are [Cin,Cout,R,S]
+                c3.v = 1; c3.r = cd.r; c3.s = cd.s;
+                c3.stride[0] = 1; c3.stride[1] = cd.stride[0]; c3.stride[2] = cd.stride[1];
+                c3.pad[0] = 0; c3.pad[1] = cd.pad[0]; c3.pad[2] = cd.pad[1];
+                if (!tr2) {
+                    c3.in_dims[0] = 1; c3.in_dims[1] = cd.cin; c3.in_dims[2] = cd.in_h; c3.in_dims[3] = cd.in_w;
+                    c3.out_dims[0] = cd.cout; c3.out_dims[1] = 1; c3.out_dims[2] = ho2; c3.out_dims[3] = wo2;
+                } else {
+                    c3.in_dims[0] = cd.cin; c3.in_dims[1] = 1; c3.in_dims[2] = cd.in_h; c3.in_dims[3] = cd.in_w;
+                    c3.out_dims[0] = 1; c3.out_dims[1] = cd.cout; c3.out_dims[2] = ho2; c3.out_dims[3] = wo2;
+                }
+                c3.weights_dtype = cd.weights_dtype; c3.weights = cd.weights; c3.bias = cd.bias;
+                c3.precision = pe2 && !strcmp(pe2, "fp16") ? RT_PREC_FP16 : RT_PREC_FP32;
+                const char* tw_env = getenv("REDTAIL_ENGINE_TOWER_SPLIT16");
+                const bool tc2 = fusion && !simt_only && !(tw_env && tw_env[0] == '0') && rt_conv3d_tc_supported(&c3) == 1;
+                int skip2 = -1;
+                if (tc2 && tr2 && nxt >= 0 && net.layers_[nxt]->d.kind == LKind::kEltwise) {
+                    // deconv -> + skip (kSUM) [-> ELU]: the ResNet18_2D decoder (resnet18_2D_513x257_net.cpp:700-760)
+                    LayerData& e = net.layers_[nxt]->d;
+                    TensorImpl* other = e.in[0] == out ? e.in[1] : e.in[0];
+                    if (other != out && (other->is_input || (other->producer >= 0 && other->producer < li))) {
+                        skip2 = other->id;
+                        done[nxt] = true; out = e.out[0]; st.name += " + " + e.name;
+                        nxt = soleConsumer(out);
+                    }
+                }
                 if (isFp32Elu(nxt)) {
                     cd.fuse_elu = 1;
                     done[nxt] = true;
                     out = net.layers_[nxt]->d.out[0];
                     st.name += " + " + net.layers_[nxt]->d.name;
                 }
-                // A 2-D convolution is a 3-D one with V = D = 1: when the channel counts fit the tensor-core tiles the
-                // tower convs run on the same tcgen05 implicit-GEMM kernel as the 3-D stack ([K,1,H,W] == [K,H,W]).
-                const char* pe2 = getenv("REDTAIL_CONV3D_PRECISION");
-                const bool simt_only = (pe2 && !strcmp(pe2, "simt")) || getenv("REDTAIL_SIMT_TOWERS") != nullptr;
-                if (fusion && !simt_only && d.kind == LKind::kConv && cd.cin % 16 == 0 && cd.cout <= 128) {
-                    rt_conv3d_desc c3{};
-                    c3.k = cd.cout; c3.v = 1; c3.c = cd.cin; c3.r = cd.r; c3.s = cd.s;
-                    c3.stride[0] = 1; c3.stride[1] = cd.stride[0]; c3.stride[2] = cd.stride[1];
-                    c3.pad[0] = 0; c3.pad[1] = cd.pad[0]; c3.pad[2] = cd.pad[1];
-                    c3.in_dims[0] = 1; c3.in_dims[1] = cd.cin; c3.in_dims[2] = cd.in_h; c3.in_dims[3] = cd.in_w;
-                    c3.out_dims[0] = cd.cout; c3.out_dims[1] = 1;
-                    c3.out_dims[2] = out->dims.d[1]; c3.out_dims[3] = out->dims.d[2];
-                    c3.weights_dtype = cd.weights_dtype; c3.weights = cd.weights; c3.bias = cd.bias;
-                    c3.precision = pe2 && !strcmp(pe2, "fp16") ? RT_PREC_FP16 : RT_PREC_FP32;
+                if (tc2) {
                     c3.fuse_elu = cd.fuse_elu;
-                    const char* tw_env = getenv("REDTAIL_ENGINE_TOWER_SPLIT16");
-                    if (!(tw_env && tw_env[0] == '0') && rt_conv3d_tc_supported(&c3) == 1) {
-                        // Deferred like the 3-D layers: the layout pass may keep the activations between consecutive tower
-                        // convolutions in RT_LAYOUT_SPLIT16 (no re-layout pass in front of the next conv).
-                        conv_steps_.emplace_back(new ConvStep());
-                        ConvStep* cs = conv_steps_.back().get();
-                        cs->desc = c3; cs->in_id = d.in[0]->id; cs->out_id = out->id; cs->name = d.name;
-                        st.out.push_back(out->id);
-                        st.conv = cs;
-                        st.run = [cs](int batch, const std::function<void*(int)>& ptr, void* ws, cudaStream_t s) {
-                            return rt_conv3d_enqueue(cs->plan, batch * cs->batch_mul, ptr(cs->in_id), nullptr, ptr(cs->out_id), ws, s);
-                        };
-                        break;
-                    }
-                    rt_conv3d_plan* p3 = nullptr;
-                    if (rt_conv3d_create(&c3, &p3) == RT_OK) {
-                        conv3d_plans_.push_back(p3);
-                        st.workspace = rt_conv3d_workspace_size(p3, max_batch_);
-                        const int in_id = d.in[0]->id, out_id = out->id;
-                        st.out.push_back(out_id);
-                        st.run = [p3, in_id, out_id](int batch, const std::function<void*(int)>& ptr, void* ws, cudaStream_t s) {
-                            return rt_conv3d_enqueue(p3, batch, ptr(in_id), nullptr, ptr(out_id), ws, s);
-                        };
-                        break;
-                    }
+                    // Deferred like the 3-D layers: the layout pass may keep the activations between consecutive convolutions
+                    // in RT_LAYOUT_SPLIT16 (no re-layout pass in front of the next conv).
+                    conv_steps_.emplace_back(new ConvStep());
+                    ConvStep* cs = conv_steps_.back().get();
+                    cs->desc = c3; cs->in_id = d.in[0]->id; cs->out_id = out->id; cs->skip_id = skip2; cs->name = d.name;
+                    if (skip2 >= 0) st.in.push_back(skip2);
+                    st.out.push_back(out->id);
+                    st.conv = cs;
+                    st.run = [cs](int batch, const std::function<void*(int)>& ptr, void* ws, cudaStream_t s) {
+                        return rt_conv3d_enqueue(cs->plan, batch * cs->batch_mul, ptr(cs->in_id), cs->skip_id >= 0 ? ptr(cs->skip_id) : nullptr,
+                                                 ptr(cs->out_id), ws, s);
+                    };
+                    break;
                 }
                 rt_conv2d_plan* plan = nullptr;
                 const int rc = rt_conv2d_create(&cd, &plan);

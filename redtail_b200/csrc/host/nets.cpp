@@ -197,9 +197,12 @@ struct rt_stereo_engine {
     ICudaEngine* engine = nullptr;
     IExecutionContext* context = nullptr;
     int h = 0, w = 0, max_batch = 1;
-    float* d_left = nullptr;      // staging for rt_stereo_execute_host
+    float* d_left = nullptr;      // staging for rt_stereo_execute_host / rt_stereo_execute_images
     float* d_right = nullptr;
     float* d_disp = nullptr;
+    uint8_t* d_img = nullptr;     // 8-bit source images (left batch, then right batch)
+    size_t d_img_bytes = 0;
+    uint16_t* d_u16 = nullptr;
     cudaStream_t stream = nullptr;
     size_t device_bytes = 0;
 };
@@ -308,12 +311,22 @@ int rt_stereo_deserialize(const void* plan, size_t plan_size, rt_stereo_engine**
     return RT_OK;
 }
 
+int rt_stereo_deserialize_batch(const void* plan, size_t plan_size, int max_batch, rt_stereo_engine** out)
+{
+    // plan header: 8-byte magic, int32 version, int32 max batch (engine.cpp, serializeNetwork)
+    if (!plan || plan_size < 16 || max_batch <= 0 || !out) { g_last_error = "rt_stereo_deserialize_batch: bad argument"; return RT_ERR_ARG; }
+    std::string copy(static_cast<const char*>(plan), plan_size);
+    const int32_t mb = max_batch;
+    memcpy(&copy[12], &mb, sizeof(mb));
+    return rt_stereo_deserialize(copy.data(), copy.size(), out);
+}
+
 void rt_stereo_destroy(rt_stereo_engine* e)
 {
     if (!e) return;
     if (e->context) e->context->destroy();
     if (e->engine) e->engine->destroy();
-    cudaFree(e->d_left); cudaFree(e->d_right); cudaFree(e->d_disp);
+    cudaFree(e->d_left); cudaFree(e->d_right); cudaFree(e->d_disp); cudaFree(e->d_img); cudaFree(e->d_u16);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -349,6 +362,50 @@ int rt_stereo_execute_host(rt_stereo_engine* e, int batch, const float* left, co
     const int rc = rt_stereo_enqueue(e, batch, e->d_left, e->d_right, e->d_disp, e->stream);
     if (rc != RT_OK) return rc;
     err = cudaMemcpyAsync(disp, e->d_disp, out_bytes * batch, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    return static_cast<int>(err);
+}
+
+int rt_stereo_execute_images(rt_stereo_engine* e, int batch, const uint8_t* left, const uint8_t* right, int src_h, int src_w,
+                             float* disp, uint16_t* disp_u16, float u16_scale)
+{
+    if (!e || !left || !right || (!disp && !disp_u16) || batch < 1 || batch > e->max_batch || src_h < e->h || src_w < e->w) return RT_ERR_ARG;
+    const size_t in_bytes = static_cast<size_t>(3) * e->h * e->w * sizeof(float);
+    const size_t out_elems = static_cast<size_t>(e->h) * e->w;
+    const size_t img_bytes = static_cast<size_t>(src_h) * src_w * 3;
+    cudaError_t err = cudaSuccess;
+    if (!e->d_left) {
+        err = cudaMalloc(reinterpret_cast<void**>(&e->d_left), in_bytes * e->max_batch);
+        if (err == cudaSuccess) err = cudaMalloc(reinterpret_cast<void**>(&e->d_right), in_bytes * e->max_batch);
+        if (err == cudaSuccess) err = cudaMalloc(reinterpret_cast<void**>(&e->d_disp), out_elems * sizeof(float) * e->max_batch);
+        if (err != cudaSuccess) return static_cast<int>(err);
+    }
+    if (e->d_img_bytes < 2 * img_bytes * e->max_batch) {
+        cudaFree(e->d_img);
+        e->d_img = nullptr; e->d_img_bytes = 0;
+        err = cudaMalloc(reinterpret_cast<void**>(&e->d_img), 2 * img_bytes * e->max_batch);
+        if (err != cudaSuccess) return static_cast<int>(err);
+        e->d_img_bytes = 2 * img_bytes * e->max_batch;
+    }
+    if (disp_u16 && !e->d_u16) {
+        err = cudaMalloc(reinterpret_cast<void**>(&e->d_u16), out_elems * sizeof(uint16_t) * e->max_batch);
+        if (err != cudaSuccess) return static_cast<int>(err);
+    }
+    uint8_t* dl = e->d_img;
+    uint8_t* dr = e->d_img + img_bytes * e->max_batch;
+    err = cudaMemcpyAsync(dl, left, img_bytes * batch, cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(dr, right, img_bytes * batch, cudaMemcpyHostToDevice, e->stream);
+    if (err != cudaSuccess) return static_cast<int>(err);
+    int rc = rt_preprocess_bgr8(dl, batch, src_h, src_w, static_cast<int64_t>(3) * src_w, e->d_left, e->h, e->w, e->stream);
+    if (rc == RT_OK) rc = rt_preprocess_bgr8(dr, batch, src_h, src_w, static_cast<int64_t>(3) * src_w, e->d_right, e->h, e->w, e->stream);
+    if (rc == RT_OK) rc = rt_stereo_enqueue(e, batch, e->d_left, e->d_right, e->d_disp, e->stream);
+    if (rc != RT_OK) return rc;
+    if (disp) err = cudaMemcpyAsync(disp, e->d_disp, out_elems * sizeof(float) * batch, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess && disp_u16) {
+        rc = rt_disparity_to_u16(e->d_disp, e->d_u16, static_cast<int64_t>(out_elems) * batch, u16_scale, e->stream);
+        if (rc != RT_OK) return rc;
+        err = cudaMemcpyAsync(disp_u16, e->d_u16, out_elems * sizeof(uint16_t) * batch, cudaMemcpyDeviceToHost, e->stream);
+    }
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
     return static_cast<int>(err);
 }

@@ -49,8 +49,12 @@ namespace {
 
 constexpr int kMaxTaps = 27;
 constexpr int kMaxClasses = 8;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;   // producer warp + MMA warp + epilogue warps
+// producer warp + two MMA-issuing warps + epilogue warps.  The two issuing warps take alternate accumulation chunks (each
+// chunk has its own TMEM buffer and its own smem stages, so no ordering between them is needed): the ~800 clk one warp spends
+// per stage on its own barrier round trips (two mbarrier.try_wait, elect/reconverge, two tcgen05.commit -- measured as the
+// 0.11 ms "barrier skeleton" of conv3D_4, profiles/r02_conv_kernel_experiments.md) overlap with the other warp's MMAs.
+constexpr int kMmaWarps = 2;
+constexpr int kThreadsOf(int epi_warps, int /*mt*/) { return 32 * (1 + kMmaWarps + epi_warps); }
 constexpr int kTileM = 128;
 
 // One pipeline stage = one A box + nr weight tiles.  nr > 1 ("row group"): the filter taps dh, dh+1, .. dh+nr-1 of a
@@ -103,6 +107,8 @@ struct TcParams {
     long long out_sn, out_sc, out_sd;   // element strides of sample, channel, depth in the dense fp32 output
     int fuse_elu;
     int out_split;           // 1: y (and skip) are RT_LAYOUT_SPLIT16, 0: dense fp32
+    int dbg;                 // timing experiments only (REDTAIL_TC_DEBUG bit mask; results are garbage): 1 = epilogue skips the
+                             // tcgen05.ld drains, 2 = no MMAs are issued, 4 = the producer moves no data, 8 = no output phase (bias/ELU/stores)
     int out_c;               // channels of the output tensor (split16 addressing)
     long long out_lo;        // split16: offset of the lo plane, in halves
     ClassInfo cls[kMaxClasses];
@@ -195,9 +201,15 @@ __device__ __forceinline__ void umma_issue_stage(int nr, uint32_t lo_a, uint32_t
 }
 
 // Epilogue register budget: each of the 8 epilogue warps owns one TMEM lane quarter (warp_id % 4) and one half of the
-// output channels, i.e. CPH = cout_pad / 2 columns of D0 (and of D1 in split mode) per thread.
-template <int CPH, bool SPLIT, int MT>
-__global__ void __launch_bounds__(kThreads, 1)
+// output channels: EW = 8 epilogue warps -> 2 column groups, EW = 16 -> 4 column groups (the output phase -- bias, skip, ELU,
+// fp16 split, stores -- and the per-chunk register adds are the throughput limit of the transposed-conv layers, which
+// have 8x less MMA work per output; twice the warps halve that work per warp).  CPH = cout_pad / (EW / 4) columns of D0
+// (and of D1 in split mode) per thread.
+template <int CPH, bool SPLIT, int MT, int EW>
+// One CTA per SM.  The register file is four 16 K banks, one per SM sub-partition: with 10 warps three of them share a bank
+// (<= 170 registers per thread, not 65536 / 320 = 204 -- a kernel compiled for 200 fails to launch with "too many resources"),
+// with 18 warps five do (<= 102); __launch_bounds__ lets ptxas apply exactly that rule.
+__global__ void __launch_bounds__(kThreadsOf(EW, MT), 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w, const __grid_constant__ TcParams p,
                    const float* __restrict__ bias, const ColInfo* __restrict__ cols, const float* __restrict__ skip,
@@ -214,7 +226,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     float* s_bias = reinterpret_cast<float*>(tmem_addr_slot + 4);
     ColInfo* s_col = reinterpret_cast<ColInfo*>(s_bias + 128);
 
-    constexpr int kCoutPad = 2 * CPH;
+    constexpr int kCoutPad = (EW / 4) * CPH;
+    constexpr int kThreads = kThreadsOf(EW, MT);
+    constexpr int kEpiBase = 1 + kMmaWarps;                  // first epilogue warp (warps 1, 2 issue the MMAs)
     constexpr int kAccCols = SPLIT ? 2 * kCoutPad : kCoutPad;   // TMEM columns of one accumulator buffer (= p.nb)
     constexpr int kBufCols = MT * kAccCols;                     // one buffer = the accumulators of the MT tiles of a job
     constexpr int kNumBuf = (512 / kBufCols) > 8 ? 8 : (512 / kBufCols);   // buffers the MMA warp may run ahead by
@@ -225,7 +239,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         if (SPLIT) prefetch_tensormap(&map_a_lo);
         prefetch_tensormap(&map_w);
         for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < kNumBuf; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
+        for (int i = 0; i < kNumBuf; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EW); }
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < kCoutPad; i += kThreads) {
@@ -257,6 +271,11 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     for (int cb = 0; cb < p.ncb; ++cb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* st = ring + static_cast<size_t>(stage) * p.stage_bytes;
+                        if (p.dbg & 4) {
+                            mbar_arrive(&full_bar[stage]);
+                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
                         mbar_arrive_expect_tx(&full_bar[stage], p.a_tx * (SPLIT ? 2 : 1) + te.nr * p.b_tx);
                         tma_load_5d(st, &map_a_hi, &full_bar[stage], cb * p.kc, cw, chh, cd, jc.n);
                         if (SPLIT) tma_load_5d(st + p.a_bytes, &map_a_lo, &full_bar[stage], cb * p.kc, cw, chh, cd, jc.n);
@@ -268,8 +287,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp < kEpiBase) {
+        // ===================== MMA issuers: warp 1 + mw issues the chunks with (chunk index & 1) == mw =====================
+        const int mw = warp - 1;
         // The tensor core accumulates in fp32 with truncation, so a long accumulation chain drifts (measured: 6e-3 px
         // of disparity over NVSmall).  Chains are therefore kept short: one chunk = p.chunk_kb K blocks (one filter
         // tap in split mode) accumulates in TMEM, then the epilogue warps add it into fp32 registers (round-to-nearest)
@@ -298,6 +318,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             if (chunk_rows >= gr) {
                 // ---- fast path: a chunk is `chunk_kb` whole stages (every layer of the nets; sub-stage chunks below) ----
                 uint32_t st_lo = (ring_addr >> 4) | (1u << 16);                  // descriptor low word of the current slot
+                uint32_t chunk_idx = 0;
                 const uint32_t st_lo0 = st_lo, stage16 = stage_bytes >> 4, a16 = a_bytes >> 4;
                 for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
                     int cls = 0;
@@ -316,10 +337,18 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         }
                         --cb_left;
                         const bool first = kb_in_chunk == 0;
+                        const bool close = (++kb_in_chunk == chunk_kb) || (kb == nkb - 1);
+                        if ((chunk_idx & 1u) != static_cast<uint32_t>(mw)) {    // the other issuing warp's chunk: only keep the counters in step
+                            if (close) {
+                                kb_in_chunk = 0; ++chunk_idx;
+                                if (++buf == kNumBuf) { buf = 0; bphase ^= 1; }
+                            }
+                            if (++stage == stages) { stage = 0; phase ^= 1; st_lo = st_lo0; } else st_lo += stage16;
+                            continue;
+                        }
                         if (first) mbar_wait(&tmem_empty[buf], bphase ^ 1);      // epilogue drained this buffer
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const bool close = (++kb_in_chunk == chunk_kb) || (kb == nkb - 1);
                         if (elect_one_sync()) {
                             const uint32_t d0 = tmem_base + static_cast<uint32_t>(buf * kBufCols);
                             const uint32_t lo_l = st_lo + a16, lo_b = st_lo + (SPLIT ? 2u : 1u) * a16;
@@ -327,7 +356,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                             // D1 is initialised by the first MMA (N covers D0|D1) when the weight tile carries W_lo rows; without them
                             // (fp16-exact weights) the A_lo x W_hi product is the first to touch D1 and must overwrite it
                             const uint32_t acc_first_lo = p.wlo ? 1u : acc_first;
-                            if (kc16 == 4)
+                            if (p.dbg & 2) {
+                            } else if (kc16 == 4)
                                 umma_issue_stage<4, MT, SPLIT, kCoutPad, kAccCols>(nr, st_lo, lo_l, lo_b, grp_a16, grp_b16, tile_a16, desc_hi, desc_b_hi, idesc_full, idesc_half, d0, acc_first, acc_first_lo);
                             else if (kc16 == 2)
                                 umma_issue_stage<2, MT, SPLIT, kCoutPad, kAccCols>(nr, st_lo, lo_l, lo_b, grp_a16, grp_b16, tile_a16, desc_hi, desc_b_hi, idesc_full, idesc_half, d0, acc_first, acc_first_lo);
@@ -338,13 +368,13 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         }
                         __syncwarp();
                         if (close) {
-                            kb_in_chunk = 0;
+                            kb_in_chunk = 0; ++chunk_idx;
                             if (++buf == kNumBuf) { buf = 0; bphase ^= 1; }
                         }
                         if (++stage == stages) { stage = 0; phase ^= 1; st_lo = st_lo0; } else st_lo += stage16;
                     }
                 }
-            } else
+            } else if (mw == 0)                          // sub-stage chunks (short chains on request): one issuing warp
             for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
                 const JobCoord jc = decode_job(p, job);
                 const int nkb = p.cls[jc.cls].ntaps * ncb;
@@ -415,7 +445,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     } else {
         // ===================== epilogue (warps 2..9) =====================
         const int q = warp & 3;                          // TMEM lane quarter this warp may access (warp_id % 4)
-        const int half = (warp - 2) >> 2;                // which half of the output channels
+        const int half = (warp - kEpiBase) >> 2;                // which group of the output channels (2 groups for EW = 8, 4 for EW = 16)
         const int m = q * 32 + lane;                     // tile row = output position within the patch
         const int hl = m / p.tw, wl = m % p.tw;
         const int col0 = half * CPH;
@@ -444,7 +474,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 mbar_wait(&tmem_full[buf], bphase);
                 tc_fence_after();
                 constexpr int LW = CPH >= 16 ? 16 : 8;   // columns per tcgen05.ld
-                constexpr int BW = CPH >= 32 ? 32 : CPH; // columns in flight per wait: all loads of a batch are issued
+                constexpr int BW = (CPH >= 64 && SPLIT) ? 16 : (CPH >= 32 ? 32 : CPH);   // columns in flight per wait (64 + 64 register
+                                                         // accumulators leave room for 16 + 16 loaded values): all loads of a batch are issued
                                                          // before the single tcgen05.wait::ld (the drain is latency-bound)
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
@@ -453,12 +484,17 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 #pragma unroll
                     for (int b0 = 0; b0 < CPH; b0 += BW) {
                         uint32_t v0[BW], v1[SPLIT ? BW : 1];
+                        if (p.dbg & 1) {
 #pragma unroll
-                        for (int c0 = 0; c0 < BW; c0 += LW) {
-                            tmem_ld<LW>(trow + b0 + c0, *reinterpret_cast<uint32_t(*)[LW]>(&v0[c0]));
-                            if (SPLIT) tmem_ld<LW>(trow + kCoutPad + b0 + c0, *reinterpret_cast<uint32_t(*)[LW]>(&v1[c0]));
+                            for (int k = 0; k < BW; ++k) { v0[k] = 0; if (SPLIT) v1[k] = 0; }
+                        } else {
+#pragma unroll
+                            for (int c0 = 0; c0 < BW; c0 += LW) {
+                                tmem_ld<LW>(trow + b0 + c0, *reinterpret_cast<uint32_t(*)[LW]>(&v0[c0]));
+                                if (SPLIT) tmem_ld<LW>(trow + kCoutPad + b0 + c0, *reinterpret_cast<uint32_t(*)[LW]>(&v1[c0]));
+                            }
+                            tmem_ld_wait();
                         }
-                        tmem_ld_wait();
 #pragma unroll
                         for (int k = 0; k < BW; ++k) {
                             acc0[mt][b0 + k] += __uint_as_float(v0[k]);
@@ -472,10 +508,16 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 if (++buf == kNumBuf) { buf = 0; bphase ^= 1; }
               }
             }
+            if (SPLIT) {                                 // result = D0 + 2^-11 D1; the D1 registers are dead from here on
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int k = 0; k < CPH; ++k) acc0[mt][k] = fmaf(acc1[mt][k], 1.f / 2048.f, acc0[mt][k]);
+            }
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
             const int hi_ = jc.h0 + mt * p.th + hl, wi_ = jc.w0 + wl;
-            if (hi_ < ci.hc && wi_ < ci.wc) {
+            if (hi_ < ci.hc && wi_ < ci.wc && !(p.dbg & 8)) {
                 const int bd = jc.d * p.out_s[0] + ci.ed, bh = hi_ * p.out_s[1] + ci.eh, bw = wi_ * p.out_s[2] + ci.ew;
                 const long long rowbase = p.out_split
                     ? jc.n * p.out_sn + ((static_cast<long long>(bd) * p.out_h + bh) * p.out_w + bw) * p.out_c
@@ -500,9 +542,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                             float v[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                v[j] = acc0[mt][k0 + j];
-                                if (SPLIT) v[j] = fmaf(acc1[mt][k0 + j], 1.f / 2048.f, v[j]);
-                                v[j] += s_bias[c0.ch + j];
+                                v[j] = acc0[mt][k0 + j] + s_bias[c0.ch + j];
                             }
                             if (skip) {
                                 const uint4 sh = __ldg(reinterpret_cast<const uint4*>(sk16 + idx));
@@ -512,18 +552,14 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[j] += fmaf(__half2float(ll[j]), 1.f / 2048.f, __half2float(hh[j]));
                             }
-                            __align__(16) __half hv[8];
-                            __align__(16) __half lv[8];
+                            if (p.fuse_elu) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float x = p.fuse_elu ? elu1(v[j]) : v[j];
-                                x = fminf(fmaxf(x, -65504.f), 65504.f);
-                                const __half hx = __float2half_rn(x);
-                                hv[j] = hx;
-                                lv[j] = __float2half_rn((x - __half2float(hx)) * 2048.f);
+                                for (int j = 0; j < 8; ++j) v[j] = elu1(v[j]);
                             }
-                            *reinterpret_cast<uint4*>(oh16 + idx) = *reinterpret_cast<const uint4*>(hv);
-                            *reinterpret_cast<uint4*>(oh16 + p.out_lo + idx) = *reinterpret_cast<const uint4*>(lv);
+                            uint4 hv, lv;
+                            split8_packed(v, hv, lv);
+                            *reinterpret_cast<uint4*>(oh16 + idx) = hv;
+                            *reinterpret_cast<uint4*>(oh16 + p.out_lo + idx) = lv;
                         }
                     }
                 } else
@@ -544,9 +580,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         if (idx[j] >= 0) {
-                            float val = acc0[mt][k0 + j];
-                            if (SPLIT) val = fmaf(acc1[mt][k0 + j], 1.f / 2048.f, val);
-                            val += s_bias[ch[j]] + sk[j];
+                            float val = acc0[mt][k0 + j] + s_bias[ch[j]] + sk[j];
                             if (p.fuse_elu) val = elu1(val);
                             out[idx[j]] = val;
                         }
@@ -661,6 +695,7 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     t->cin_src = cin_src;
     p.split = split;
     p.wlo = wlo ? 1 : 0;
+    p.dbg = getenv("REDTAIL_TC_DEBUG") ? atoi(getenv("REDTAIL_TC_DEBUG")) : 0;
     p.kc = cin >= 64 ? 64 : cin;
     if (const char* e = getenv("REDTAIL_TC_KC")) {           // experiment switch: narrower K blocks = smaller, more numerous stages
         const int kc = atoi(e);
@@ -993,28 +1028,40 @@ int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const f
     // 3. main kernel
     int grid = num_sms();
     if (grid > p.njobs) grid = p.njobs;
-#define RT_LAUNCH_UMMA(CPH, SPL, MTT)                                                                                    \
+#define RT_LAUNCH_UMMA(CPH, SPL, MTT, EWW)                                                                               \
     do {                                                                                                              \
         static bool attr_set[64] = {};            /* per device: the attribute belongs to the device's copy of the kernel */ \
         int dev_ = 0;                                                                                                 \
         RT_CUDA(cudaGetDevice(&dev_));                                                                                \
         if (dev_ < 0 || dev_ >= 64 || !attr_set[dev_]) {                                                              \
-            RT_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<CPH, SPL, MTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            RT_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<CPH, SPL, MTT, EWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
             if (dev_ >= 0 && dev_ < 64) attr_set[dev_] = true;                                                        \
         }                                                                                                             \
-        conv3d_umma_kernel<CPH, SPL, MTT><<<grid, kThreads, t->smem_bytes, s>>>(ma_hi, ma_lo, t->map_w, p, plan->bias, t->d_cols, skip, y); \
+        conv3d_umma_kernel<CPH, SPL, MTT, EWW><<<grid, kThreadsOf(EWW, MTT), t->smem_bytes, s>>>(ma_hi, ma_lo, t->map_w, p, plan->bias, t->d_cols, skip, y); \
     } while (0)
+    // 16 epilogue warps (4 column groups) from 32 accumulator columns up; REDTAIL_TC_EW=8 keeps 8.
+    static const bool ew8 = getenv("REDTAIL_TC_EW") && atoi(getenv("REDTAIL_TC_EW")) == 8;
     switch (p.cout_pad) {
         case 16:
-            if (p.mt == 2) { if (p.split) RT_LAUNCH_UMMA(8, true, 2); else RT_LAUNCH_UMMA(8, false, 2); }
-            else { if (p.split) RT_LAUNCH_UMMA(8, true, 1); else RT_LAUNCH_UMMA(8, false, 1); }
+            if (p.mt == 2) { if (p.split) RT_LAUNCH_UMMA(8, true, 2, 8); else RT_LAUNCH_UMMA(8, false, 2, 8); }
+            else { if (p.split) RT_LAUNCH_UMMA(8, true, 1, 8); else RT_LAUNCH_UMMA(8, false, 1, 8); }
             break;
         case 32:
-            if (p.mt == 2) { if (p.split) RT_LAUNCH_UMMA(16, true, 2); else RT_LAUNCH_UMMA(16, false, 2); }
-            else { if (p.split) RT_LAUNCH_UMMA(16, true, 1); else RT_LAUNCH_UMMA(16, false, 1); }
+            if (ew8) {
+                if (p.mt == 2) { if (p.split) RT_LAUNCH_UMMA(16, true, 2, 8); else RT_LAUNCH_UMMA(16, false, 2, 8); }
+                else { if (p.split) RT_LAUNCH_UMMA(16, true, 1, 8); else RT_LAUNCH_UMMA(16, false, 1, 8); }
+            } else {
+                if (p.mt == 2) { if (p.split) RT_LAUNCH_UMMA(8, true, 2, 16); else RT_LAUNCH_UMMA(8, false, 2, 16); }
+                else { if (p.split) RT_LAUNCH_UMMA(8, true, 1, 16); else RT_LAUNCH_UMMA(8, false, 1, 16); }
+            }
             break;
-        case 64:  if (p.split) RT_LAUNCH_UMMA(32, true, 1); else RT_LAUNCH_UMMA(32, false, 1); break;
-        case 128: if (p.split) RT_LAUNCH_UMMA(64, true, 1); else RT_LAUNCH_UMMA(64, false, 1); break;
+        case 64:
+            if (ew8) { if (p.split) RT_LAUNCH_UMMA(32, true, 1, 8); else RT_LAUNCH_UMMA(32, false, 1, 8); }
+            else { if (p.split) RT_LAUNCH_UMMA(16, true, 1, 16); else RT_LAUNCH_UMMA(16, false, 1, 16); }
+            break;
+        case 128:           // 128 + 128 accumulator columns: 64 + 64 per thread with 8 warps fit in 200 registers; 16 warps (112) spill
+            if (p.split) RT_LAUNCH_UMMA(64, true, 1, 8); else RT_LAUNCH_UMMA(64, false, 1, 8);
+            break;
         default: return RT_ERR_UNSUPPORTED;
     }
 #undef RT_LAUNCH_UMMA

@@ -70,23 +70,6 @@ cvconv_edge_kernel(const float* __restrict__ right, const float* __restrict__ w_
     }
 }
 
-// ELU with expm1 accurate to ~1 ulp of max(|result|, 2^-3) at a third of expm1f's instruction count: a degree-6 Taylor
-// polynomial on (-1/8, 0] (truncation error < 1e-9 relative), ex2.approx - 1 below (absolute error ~1e-7 on a result of
-// magnitude >= 0.117).
-__device__ __forceinline__ float elu_fast(float v) {
-    float p = 1.f / 720.f;
-    p = fmaf(p, v, 1.f / 120.f);
-    p = fmaf(p, v, 1.f / 24.f);
-    p = fmaf(p, v, 1.f / 6.f);
-    p = fmaf(p, v, 0.5f);
-    p = fmaf(p, v * v, v);
-    float e2;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(v * 1.4426950408889634f));
-    const float ex = e2 - 1.f;
-    const float neg = v > -0.125f ? p : ex;
-    return v > 0.f ? v : neg;
-}
-
 // fp32 x8 -> split16 (hi, lo) 16-byte vectors; `lo_clamp` false when the values are known to be >= -65504.
 __device__ __forceinline__ void split_store8_fast(const float (&v)[8], __half* hi, __half* lo) {
     __align__(16) __half2 hv[4];
@@ -161,7 +144,7 @@ cvconv_combine_kernel(const float* __restrict__ a, const float* __restrict__ cc,
         }
         if (fuse_elu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) val[j] = elu_fast(val[j]);
+            for (int j = 0; j < 8; ++j) val[j] = elu1_approx(val[j]);
         }
         if (kSplitOut) {
             __half* hi = static_cast<__half*>(out) + static_cast<long long>(n) * 2 * plane;

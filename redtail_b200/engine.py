@@ -37,14 +37,18 @@ class StereoEngine:
         return buf.raw
 
     @classmethod
-    def deserialize(cls, plan):
-        """Engine from a plan (IRuntime::deserializeCudaEngine + StereoDnnPluginFactory); no weight file needed."""
+    def deserialize(cls, plan, max_batch=None):
+        """Engine from a plan (IRuntime::deserializeCudaEngine + StereoDnnPluginFactory); no weight file needed.
+        max_batch overrides the batch size the plan was written with."""
         if not torch.cuda.is_available():
             raise RedtailError("StereoEngine needs a CUDA device (there is no CPU path)")
         self = cls.__new__(cls)
         self.lib = engine_lib()
         self._e = C.c_void_p()
-        rc = self.lib.rt_stereo_deserialize(plan, len(plan), C.byref(self._e))
+        if max_batch is None:
+            rc = self.lib.rt_stereo_deserialize(plan, len(plan), C.byref(self._e))
+        else:
+            rc = self.lib.rt_stereo_deserialize_batch(plan, len(plan), int(max_batch), C.byref(self._e))
         if rc != 0:
             raise RedtailError("rt_stereo_deserialize failed (%d): %s" % (rc, self.lib.rt_stereo_last_error().decode()))
         self.h = self.w = self.max_batch = None      # taken from the plan by the library
@@ -70,6 +74,19 @@ class StereoEngine:
         if rc != 0:
             raise RedtailError("rt_stereo_execute_host failed (%d): %s" % (rc, self.lib.rt_stereo_last_error().decode()))
         return out
+
+    def execute_images(self, left_bgr, right_bgr, out=None, out_u16=None, u16_scale=256.0):
+        """Host uint8 [N,H_src,W_src,3] BGR images (cv::imread layout) -> disparity: 8-bit H2D, GPU pre-processing
+        (INTER_AREA resize to the network size, RGB, CHW, /255), inference, D2H.  out: float32 [N,H,W] host tensor and/or
+        out_u16: uint16 [N,H,W] (KITTI-style PNG payload); synchronous."""
+        assert left_bgr.dtype == torch.uint8 and left_bgr.dim() == 4 and left_bgr.shape[3] == 3 and left_bgr.is_contiguous()
+        n, sh, sw, _ = left_bgr.shape
+        rc = self.lib.rt_stereo_execute_images(self._e, n, C.c_void_p(left_bgr.data_ptr()), C.c_void_p(right_bgr.data_ptr()), sh, sw,
+                                               C.c_void_p(out.data_ptr() if out is not None else 0),
+                                               C.c_void_p(out_u16.data_ptr() if out_u16 is not None else 0), float(u16_scale))
+        if rc != 0:
+            raise RedtailError("rt_stereo_execute_images failed (%d): %s" % (rc, self.lib.rt_stereo_last_error().decode()))
+        return out if out is not None else out_u16
 
     def profile(self, left, right):
         """-> list of (layer name, ms), measured with CUDA events around every engine step."""

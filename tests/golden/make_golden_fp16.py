@@ -51,14 +51,17 @@ def main():
     if "--skip-disp" in sys.argv:
         return
     left, right = oio.load_sample_pair()
-    for net, (h, w) in (("nvtiny", (161, 513)), ("nvsmall", (321, 1025))):
+    for net, (h, w) in (() if "--only-2d-1025" in sys.argv else (("nvtiny", (161, 513)), ("nvsmall", (321, 1025)))):
         wts = oio.read_weights("/tmp/make_golden_fp16_%s.bin" % net, np.float16)
         l, r = oio.resize_pair(left, right, h, w)
         disp = nets.stereo_forward(net, wts, l, r, dtype=torch.float64)
         np.save(os.path.join(HERE, "disp_%s_%dx%d_fp16w_f64oracle.npy" % (net, w, h)), disp.astype(np.float32))
         print(net, disp.shape, float(disp.min()), float(disp.max()))
     driver = os.path.join(ROOT, "dropin", "_ref", "nvstereo_net_driver")
-    for net, (h, w) in (("resnet18_2D", (257, 513)), ("resnet18", (321, 1025))):
+    cases = (("resnet18_2D", (257, 513)), ("resnet18_2D", (321, 1025)), ("resnet18", (321, 1025)))
+    if "--only-2d-1025" in sys.argv:
+        cases = cases[1:2]
+    for net, (h, w) in cases:
         tmp = "/tmp/make_golden_fp16_%s" % net
         np.zeros(3 * h * w, dtype=np.float32).tofile(tmp + ".z")
         subprocess.run([driver, net, str(w), str(h), oio.weights_path(net), tmp + ".z", tmp + ".z", tmp + ".plan", "dump"], check=True)

@@ -61,3 +61,24 @@ def test_preprocess_rejects_upscaling():
     from redtail_b200 import ops
     with pytest.raises(ops.RedtailError):
         ops.preprocess_bgr8(torch.zeros((1, 8, 8, 3), dtype=torch.uint8, device="cuda"), 16, 16)
+
+
+def test_engine_execute_images_end_to_end(tmp_path):
+    """rt_stereo_execute_images: 8-bit BGR host images -> GPU pre-processing -> NVTiny -> disparity + 16-bit PNG payload, equal
+    to running the same steps one by one (ops.preprocess_bgr8, the engine, ops.disparity_to_u16)."""
+    from redtail_b200 import StereoEngine, ops
+    h, w = 161, 513
+    l, r = oio.load_sample_pair()                                   # [3,321,1025] RGB in [0,1]
+    to_bgr8 = lambda a: np.ascontiguousarray(np.clip(np.rint(a[::-1].transpose(1, 2, 0) * 255.0), 0, 255).astype(np.uint8))
+    lb, rb = torch.from_numpy(to_bgr8(l)[None]), torch.from_numpy(to_bgr8(r)[None])    # 321x1025 sources, resized 2:1 (area)
+    eng = StereoEngine("nvtiny", h, w, oio.weights_path("nvtiny"))
+    disp = torch.empty((1, h, w), dtype=torch.float32).pin_memory()
+    u16 = torch.empty((1, h, w), dtype=torch.uint16).pin_memory()
+    eng.execute_images(lb.pin_memory(), rb.pin_memory(), out=disp, out_u16=u16)
+    lt, rt = ops.preprocess_bgr8(lb.cuda(), h, w), ops.preprocess_bgr8(rb.cuda(), h, w)
+    ref = eng(lt, rt)
+    assert np.abs(disp.numpy() - ref.cpu().numpy()).max() <= 1e-6
+    assert np.array_equal(u16.numpy(), ops.disparity_to_u16(ref).cpu().numpy())
+    assert 1.0 < float(ref.mean()) < 60.0                           # a real disparity map, not zeros
+    ops.write_png16(tmp_path / "disp.png", u16.numpy()[0])
+    assert os.path.getsize(tmp_path / "disp.png") > 2 * h * w

@@ -23,6 +23,19 @@ $CXX -o "$OUT/nvstereo_tests" "$OUT/tests_main.o" "$OUT/gtest_lite.o" $LIB
 # sample_app/main.cpp does and runs the engine on raw .bin images.
 $CXX $INC -I"$REF/sample_app" -c "$ROOT/tools/dropin/net_driver.cpp" -o "$OUT/net_driver.o"
 $CXX -o "$OUT/nvstereo_net_driver" "$OUT/net_driver.o" "$OUT"/*_net.o $LIB
+# Plans of the reference's ResNet networks at the resolution of BASELINE.json's configs, written host-only by the
+# reference's own builders (net driver `dump` mode): what bench.py --config resnet18 / resnet18_2d runs.
+mkdir -p "$OUT/plans"
+W="$ROOT/tests/golden/weights"
+head -c $((3*321*1025*4)) /dev/zero > "$OUT/plans/zero.bin"
+for n in resnet18 resnet18_2D; do
+  (cd "$ROOT" && python -c "from oracle import io; io.write_fp16_weights('$W/${n}_fp32.bin', '$OUT/plans/${n}_fp16.bin')")
+  LD_LIBRARY_PATH="$ROOT/redtail_b200/lib" "$OUT/nvstereo_net_driver" $n 1025 321 "$W/${n}_fp32.bin" "$OUT/plans/zero.bin" "$OUT/plans/zero.bin" "$OUT/plans/${n}_1025x321_fp32.plan" dump > /dev/null
+  LD_LIBRARY_PATH="$ROOT/redtail_b200/lib" "$OUT/nvstereo_net_driver" $n 1025 321 "$OUT/plans/${n}_fp16.bin" "$OUT/plans/zero.bin" "$OUT/plans/zero.bin" "$OUT/plans/${n}_1025x321_fp16.plan" dump fp16 > /dev/null
+  rm -f "$OUT/plans/${n}_fp16.bin"
+done
+rm -f "$OUT/plans/zero.bin"
+ls -la "$OUT/plans"
 # The reference's sample application itself, UNCHANGED (sample_app/main.cpp: PNG in, engine, binary + 16-bit PNG out),
 # against the cv:: stand-in of tools/dropin/include/opencv2 (OpenCV's C++ headers are not in this image).
 $CXX $INC -I"$REF/sample_app" -c "$REF/sample_app/main.cpp" -o "$OUT/main.o"
