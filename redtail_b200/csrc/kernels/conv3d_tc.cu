@@ -339,6 +339,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         const bool first = kb_in_chunk == 0;
                         const bool close = (++kb_in_chunk == chunk_kb) || (kb == nkb - 1);
                         if ((chunk_idx & 1u) != static_cast<uint32_t>(mw)) {    // the other issuing warp's chunk: only keep the counters in step
+                            // ... and observe the stage's full barrier: an mbarrier has ONE phase bit, so a warp that waited for
+                            // phase p+1 of a slot before phase p had completed would see "complete" at once (parity aliasing).
+                            // Watching every phase of every slot in order keeps both warps within one phase of each barrier.
+                            mbar_wait(&full_bar[stage], phase);
                             if (close) {
                                 kb_in_chunk = 0; ++chunk_idx;
                                 if (++buf == kNumBuf) { buf = 0; bphase ^= 1; }
