@@ -120,6 +120,9 @@ typedef struct {
     int out_layout;          /* layout of y; `skip`, when given, uses the same layout as y                          */
     int pad_end_d;           /* conv only: this many virtual zero planes follow the input (fuses PaddingPlugin);
                                 in_dims[0] excludes them -- on the tensor-core path they are TMA out-of-bounds fill */
+    int fuse_softargmax;     /* transposed, C == 1 only: 0 none, 1 soft-argmin, 2 soft-argmax over the (sliced) output planes
+                                (fuses SoftargmaxPlugin, lib/softargmax_plugin.cpp:167-205): y is then [n,Hx,Wx] fp32 and the
+                                [Dx,1,Hx,Wx] volume is never written.  Needs RT_PREC_FP32, a split16 input, K == 32.       */
 } rt_conv3d_desc;
 
 int  rt_conv3d_create(const rt_conv3d_desc* desc, rt_conv3d_plan** plan);   /* repacks + uploads weights        */

@@ -426,6 +426,7 @@ struct Step {
     ConvStep* conv = nullptr;                                   // set for fused 3-D convolution steps
     int costvol_c = 0, costvol_h = 0, costvol_w = 0, costvol_d = 0;   // set for concat cost-volume steps
     bool is_transform = false;                                  // Transform{1,0,2,3} plugin step
+    int softargmax = 0;                                         // SoftargmaxPlugin step: 1 = kMin, 2 = kMax (may fuse into its producer)
     bool dropped = false;
     // ptr(id) resolves a tensor id to its device pointer for this execution.
     std::function<int(int batch, const std::function<void*(int)>& ptr, void* workspace, cudaStream_t)> run;
@@ -913,6 +914,7 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                     st.costvol_d = op->max_disparity;
                 }
                 if (fusion && op && op->kind == OpKind::kTransform) st.is_transform = true;
+                if (fusion && op && op->kind == OpKind::kSoftargmax) st.softargmax = op->sm_type == redtail::tensorrt::SoftargmaxType::kMin ? 1 : 2;
                 // ---- redtail plugins declared kHALF (the fp16 builders: resnet18_2D_513x257_net.cpp with data_type = kHALF) ----
                 // The graph's tensors are fp32; instead of wrapping the plugin in fp32<->fp16 reformat passes (what TensorRT
                 // does, and what rounds every activation to fp16) the engine runs the same kernel on the fp32 tensors: one
@@ -1172,6 +1174,29 @@ bool EngineImpl::assignLayoutsAndCreatePlans(bool fusion)
                 const ConvStep* cs = steps_[si].conv;
                 if (cs && cs->skip_id >= 0 && split[cs->out_id] && !split[cs->skip_id]) { split[cs->out_id] = 0; changed = true; }
             }
+        }
+    }
+    // Conv3DTranspose (-> Slice) with ONE output channel whose only consumer is the Softargmax plugin (the last two layers of
+    // every stereo net, nvsmall_1025x321_net.cpp:398-420): one kernel, the [Dx,1,Hx,Wx] volume is never written
+    // (deconv_softargmax.cu).  REDTAIL_ENGINE_DSA=0 keeps the two steps.
+    const char* dsa_env = getenv("REDTAIL_ENGINE_DSA");
+    if (fusion && !(dsa_env && dsa_env[0] == '0')) {
+        for (int si = 0; si < ns; ++si) {
+            Step& sm = steps_[si];
+            if (!sm.softargmax || sm.dropped || sm.in.size() != 1 || sm.out.size() != 1) continue;
+            const int t = sm.in[0];
+            if (producer[t] < 0 || consumers[t].size() != 1 || slots_[t].binding >= 0) continue;
+            Step& ps = steps_[producer[t]];
+            ConvStep* cs = ps.conv;
+            if (!cs || cs->cvfused || cs->out_id != t || cs->skip_id >= 0 || cs->batch_mul != 1 || !split[cs->in_id] || split[t]) continue;
+            rt_conv3d_desc d = cs->desc;
+            d.in_layout = RT_LAYOUT_SPLIT16; d.out_layout = RT_LAYOUT_DENSE; d.fuse_softargmax = sm.softargmax;
+            if (rt_conv3d_tc_supported(&d) != 1) continue;
+            cs->desc.fuse_softargmax = sm.softargmax;
+            cs->out_id = sm.out[0];
+            ps.out = sm.out;
+            ps.name += " + " + sm.name;
+            sm.dropped = true;
         }
     }
     int nsplit = 0;

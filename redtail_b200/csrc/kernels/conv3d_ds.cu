@@ -1,0 +1,382 @@
+// Depth-stationary 3-D convolution on tcgen05 for the 32 -> 32 channel, 3x3x3, stride-1 layers at full cost-volume resolution
+// (NVSmall conv3D_2 -- 24 % of the step in round 1 -- and ResNet-18's conv3D_1b): Conv3DPlugin::enqueue
+// (lib/conv3d_plugin.cpp:186-279) + Transform + ELU of the builders (sample_app/nvsmall_1025x321_net.cpp conv3D_2*).
+//
+// Why a second kernel.  With Cout = 32 the generic kernel (conv3d_tc.cu) issues MMAs of N = 64 / 32: the 4 KB A tile is re-read
+// from shared memory for every 32 output channels, an MMA lasts 32 clk -- about what it costs to issue -- and every pipeline
+// stage re-loads its weight tiles (profiles/r02_conv_kernel_experiments.md).  Here one A tile (input plane p, tap dh,dw) feeds
+// the THREE output planes p+1, p, p-1 in one MMA: the weights of the three filter planes are stacked along GEMM-N
+// (N = 3 x 64 with [W_hi ; W_lo] rows, + N = 96 for the A_lo x W_hi product), so A is read once per 96 output columns, the
+// MMAs last 96 / 48 clk, and all 27 weight tiles (108 KB) stay resident in shared memory for the life of the CTA -- a pipeline
+// stage is just two 10 KB activation boxes (hi, lo), five stages deep.
+//
+//   job    = one 8 x 16 patch of output positions, ALL depth planes (persistent CTAs, static round-robin over the patches)
+//   stage  = input plane p, filter column dw: one TMA box [10 rows x 16 positions x 32 ch] per fp16 plane (hi, lo); the three
+//            filter rows dh read it at row offsets 0, 1, 2 KB (same trick as the generic kernel's row groups)
+//   chunk  = one stage = 6 MMA K-steps accumulated in TMEM (the tensor core's fp32 accumulation truncates, so chains are kept
+//            as short as in the generic kernel), then added with round-to-nearest into fp32 registers by the epilogue warps
+//   TMEM   = 2 buffers x 192 columns: [D0(v=0) D0(v=1) D0(v=2) | D1(v=0) D1(v=1) D1(v=2)], v = filter plane; column block v of
+//            input plane p belongs to output plane p + 1 - v
+//   epilogue registers = three rotating accumulator sets (output planes p-1, p, p+1; set = plane mod 3, the plane loop is
+//            unrolled by 3 so the rotation is static); when input plane p is done, output plane p-1 is complete:
+//            D0 + 2^-11 D1 + bias -> ELU -> fp16 hi/lo split -> two 16-byte stores (RT_LAYOUT_SPLIT16).
+//
+// Numerics: the sequence of products and of fp32 additions per output element is exactly the generic kernel's (filter plane,
+// then filter column, then filter row, then K-step; one chunk per (plane, column)), so the two kernels agree bit for bit --
+// tests/test_gpu_plugins.py::test_conv3d_depth_stationary_bitexact -- and the parity of the nets is unchanged.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "conv3d_internal.h"
+#include "tma.cuh"
+
+namespace rt {
+namespace {
+
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = 32 * (2 + kEpiWarps);      // warp 0: TMA producer, warp 1: MMA issuer, warps 2..17: epilogue
+constexpr int kStages = 5;
+constexpr int kTh = 8, kTw = 16;                    // 128 output positions
+constexpr int kCin = 32, kCoutPad = 32;
+constexpr int kABytes = (kTh + 2) * kTw * kCin * 2; // 10 240: one activation box (already a 1 KB multiple)
+constexpr int kStageBytes = 2 * kABytes;            // hi + lo
+constexpr int kBufCols = 6 * kCoutPad;              // 192 TMEM columns per accumulator buffer
+constexpr int kNumBuf = 2;
+
+struct DsParams {
+    int njobs, tiles_w, tiles_per_sample;
+    int depth, out_h, out_w;
+    int cout;
+    int fuse_elu;
+    int b_tile_bytes;          // one (dh, dw) weight tile: nb1 rows x 64 B
+    int nb1;                   // 192 ([W_hi ; W_lo] x 3 filter planes) or 96 (fp16-exact weights, W_lo == 0)
+    long long out_sn, out_lo;  // halves per sample (hi + lo plane), offset of the lo plane
+};
+
+struct DsPlanImpl {
+    DsParams p{};
+    __half* w_dev = nullptr;
+    CUtensorMap map_w{};
+    bool wlo = true;
+    int in_d = 0, in_h = 0, in_w = 0;
+    size_t in_elems = 0;
+    int smem_bytes = 0;
+};
+
+__device__ __forceinline__ void zero16(float (&a)[16]) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = 0.f;
+}
+
+// Output phase of one finished plane: D0 + D1 / 2048 + bias -> ELU -> split16 stores of this thread's 8 channels.
+__device__ __forceinline__ void emit_plane(const DsParams& p, const float (&a)[16], const float* s_bias, __half* out, int n, int q,
+                                           int h, int w, int g) {
+    if (h >= p.out_h || w >= p.out_w || g * 8 >= p.cout) return;
+    const long long idx = n * p.out_sn + ((static_cast<long long>(q) * p.out_h + h) * p.out_w + w) * p.cout + g * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        v[j] = fmaf(a[8 + j], 1.f / 2048.f, a[j]) + s_bias[g * 8 + j];
+        if (p.fuse_elu) v[j] = elu1(v[j]);
+    }
+    uint4 hv, lv;
+    split8_packed(v, hv, lv);
+    *reinterpret_cast<uint4*>(out + idx) = hv;
+    *reinterpret_cast<uint4*>(out + p.out_lo + idx) = lv;
+}
+
+template <bool WLO>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3d_ds_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ DsParams p, const float* __restrict__ bias,
+                 __half* __restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* wsm = smem;                                              // 9 resident weight tiles
+    uint8_t* ring = smem + 9 * p.b_tile_bytes;                        // kStages x (hi box | lo box)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + kStages * kStageBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + kNumBuf;
+    uint64_t* w_bar = tmem_empty + kNumBuf;
+    uint32_t* tmem_addr_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+    float* s_bias = reinterpret_cast<float*>(tmem_addr_slot + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        prefetch_tensormap(&map_a_hi);
+        prefetch_tensormap(&map_a_lo);
+        prefetch_tensormap(&map_w);
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < kNumBuf; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
+        mbar_init(w_bar, 1);
+        fence_barrier_init();
+    }
+    if (threadIdx.x < kCoutPad) s_bias[threadIdx.x] = static_cast<int>(threadIdx.x) < p.cout ? bias[threadIdx.x] : 0.f;
+    if (warp == 1) tmem_alloc<512>(tmem_addr_slot);      // one CTA per SM (> half of the shared memory): the whole TMEM
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (*tmem_addr_slot != 0u) __trap();                 // addresses below are compile-time offsets from column 0
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w_bar, 9 * p.b_tile_bytes);
+            for (int t = 0; t < 9; ++t) tma_load_2d(wsm + t * p.b_tile_bytes, &map_w, w_bar, 0, t * p.nb1);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
+                const int n = job / p.tiles_per_sample, r = job - n * p.tiles_per_sample;
+                const int w0 = (r % p.tiles_w) * kTw, h0 = (r / p.tiles_w) * kTh;
+                for (int pl = 0; pl < p.depth; ++pl) {
+                    for (int dw = -1; dw <= 1; ++dw) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* st = ring + stage * kStageBytes;
+                        mbar_arrive_expect_tx(&full_bar[stage], 2 * kABytes);
+                        tma_load_5d(st, &map_a_hi, &full_bar[stage], 0, w0 + dw, h0 - 1, pl, n);
+                        tma_load_5d(st + kABytes, &map_a_lo, &full_bar[stage], 0, w0 + dw, h0 - 1, pl, n);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t pitch = kCin * 2;                                       // 64-byte operand rows, SWIZZLE_64B
+        // descriptor high word: SBO (8 rows) | version 1 (bit 46) | swizzle code 4 = 64B (bits 61-63)
+        constexpr uint64_t desc_hi = (static_cast<uint64_t>(((8u * pitch) >> 4) | (1u << 14) | (4u << 29))) << 32;
+        constexpr uint32_t idesc1 = umma_idesc_f16(128, WLO ? 6 * kCoutPad : 3 * kCoutPad);
+        constexpr uint32_t idesc2 = umma_idesc_f16(128, 3 * kCoutPad);
+        constexpr uint32_t row16 = (kTw * pitch) >> 4;                             // one patch row of A, in 16-byte units
+        const uint32_t ring_lo = (smem_u32(ring) >> 4) | (1u << 16);               // descriptor low word: start >> 4 | LBO = 1
+        const uint32_t w_lo = (smem_u32(wsm) >> 4) | (1u << 16);
+        const uint32_t bt16 = static_cast<uint32_t>(p.b_tile_bytes) >> 4;
+        mbar_wait(w_bar, 0);                                                       // the resident weights have landed
+        int stage = 0, buf = 0;
+        uint32_t phase = 0, bphase = 0;
+        for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
+            for (int pl = 0; pl < p.depth; ++pl) {
+#pragma unroll
+                for (int dwi = 0; dwi < 3; ++dwi) {
+                    mbar_wait(&tmem_empty[buf], bphase ^ 1);                       // epilogue drained this buffer
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t d0 = static_cast<uint32_t>(buf * kBufCols);
+                        const uint32_t a_hi = ring_lo + static_cast<uint32_t>(stage) * (kStageBytes >> 4);
+                        const uint32_t a_lo = a_hi + (kABytes >> 4);
+#pragma unroll
+                        for (int dh = 0; dh < 3; ++dh) {
+                            const uint32_t b = w_lo + static_cast<uint32_t>(dh * 3 + dwi) * bt16;
+#pragma unroll
+                            for (int kk = 0; kk < 2; ++kk) {                       // +32 bytes = one K = 16 slice inside the swizzle atom
+                                const uint32_t first = (dh == 0 && kk == 0) ? 0u : 1u;
+                                umma_f16(d0, desc_hi | (a_hi + dh * row16 + 2 * kk), desc_hi | (b + 2 * kk), idesc1, first);
+                                // A_lo x W_hi adds into D1; with W_lo rows D1 was initialised by the MMA above
+                                umma_f16(d0 + 3 * kCoutPad, desc_hi | (a_lo + dh * row16 + 2 * kk), desc_hi | (b + 2 * kk), idesc2, WLO ? 1u : first);
+                            }
+                        }
+                        umma_commit(&empty_bar[stage]);
+                        umma_commit(&tmem_full[buf]);
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++buf == kNumBuf) { buf = 0; bphase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access (warp_id % 4)
+        const int g = (warp - 2) >> 2;                   // 8-channel group
+        const int m = q * 32 + lane;
+        const int hl = m / kTw, wl = m % kTw;
+        const uint32_t lane_base = (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * 8);
+        int buf = 0;
+        uint32_t bphase = 0;
+        for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
+            const int n = job / p.tiles_per_sample, r = job - n * p.tiles_per_sample;
+            const int w = (r % p.tiles_w) * kTw + wl, h = (r / p.tiles_w) * kTh + hl;
+            float acc[3][16];                            // [output plane mod 3][D0 x 8 | D1 x 8]
+            zero16(acc[0]); zero16(acc[1]); zero16(acc[2]);
+            for (int pl0 = 0; pl0 < p.depth; pl0 += 3) {
+#pragma unroll
+                for (int rr = 0; rr < 3; ++rr) {
+                    const int pl = pl0 + rr;
+                    if (pl < p.depth) {
+                        for (int dwi = 0; dwi < 3; ++dwi) {
+                            mbar_wait(&tmem_full[buf], bphase);
+                            tc_fence_after();
+                            const uint32_t t0 = lane_base + static_cast<uint32_t>(buf * kBufCols);
+#pragma unroll
+                            for (int v = 0; v < 3; ++v) {                          // filter plane v -> output plane pl + 1 - v
+                                uint32_t x0[8], x1[8];
+                                tmem_ld8(t0 + v * kCoutPad, x0);
+                                tmem_ld8(t0 + 3 * kCoutPad + v * kCoutPad, x1);
+                                tmem_ld_wait();
+                                float (&a)[16] = acc[(rr + 4 - v) % 3];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    a[k] += __uint_as_float(x0[k]);
+                                    a[8 + k] += __uint_as_float(x1[k]);
+                                }
+                            }
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                            if (++buf == kNumBuf) { buf = 0; bphase ^= 1; }
+                        }
+                        // input plane pl is done: output plane pl - 1 (set (rr + 2) % 3) is complete
+                        if (pl >= 1) emit_plane(p, acc[(rr + 2) % 3], s_bias, out, n, pl - 1, h, w, g);
+                        zero16(acc[(rr + 2) % 3]);
+                    }
+                }
+            }
+            // the last output plane (it has no input plane after it)
+            const int last = p.depth - 1;
+            switch (last % 3) {
+                case 0: emit_plane(p, acc[0], s_bias, out, n, last, h, w, g); break;
+                case 1: emit_plane(p, acc[1], s_bias, out, n, last, h, w, g); break;
+                default: emit_plane(p, acc[2], s_bias, out, n, last, h, w, g); break;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(0u);
+}
+
+uint16_t f2h(float f) {
+    __half h = __float2half_rn(f);
+    uint16_t b;
+    memcpy(&b, &h, 2);
+    return b;
+}
+float h2f(uint16_t b) {
+    __half h;
+    memcpy(&h, &b, 2);
+    return __half2float(h);
+}
+
+}  // namespace
+
+bool ds_shape_supported(const rt_conv3d_desc& d) {
+    if (d.transposed || d.precision != RT_PREC_FP32) return false;
+    if (d.v != 3 || d.r != 3 || d.s != 3) return false;
+    for (int i = 0; i < 3; ++i)
+        if (d.stride[i] != 1 || d.pad[i] != 1) return false;
+    if (d.pad_end_d != 0) return false;
+    if (d.in_layout != RT_LAYOUT_SPLIT16 || d.out_layout != RT_LAYOUT_SPLIT16) return false;
+    if (d.c != kCin || d.k > kCoutPad || d.k <= 16 || d.k % 8 != 0) return false;
+    if (d.in_dims[0] < 2) return false;
+    if (const char* e = getenv("REDTAIL_TC_DS")) return atoi(e) != 0;
+    return true;
+}
+
+int ds_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w) {
+    const rt_conv3d_desc& d = plan->desc;
+    if (!ds_shape_supported(d) || !get_encode_tiled()) return RT_ERR_UNSUPPORTED;
+    DsPlanImpl* t = new DsPlanImpl();
+    DsParams& p = t->p;
+    t->in_d = d.in_dims[0]; t->in_h = d.in_dims[2]; t->in_w = d.in_dims[3];
+    t->in_elems = static_cast<size_t>(kCin) * t->in_d * t->in_h * t->in_w;
+    p.depth = t->in_d; p.out_h = t->in_h; p.out_w = t->in_w;
+    p.cout = d.k;
+    p.fuse_elu = d.fuse_elu;
+    p.tiles_w = (p.out_w + kTw - 1) / kTw;
+    p.tiles_per_sample = p.tiles_w * ((p.out_h + kTh - 1) / kTh);
+    const long long plane_elems = static_cast<long long>(p.depth) * p.out_h * p.out_w * p.cout;
+    p.out_sn = 2 * plane_elems;
+    p.out_lo = plane_elems;
+    bool wlo = false;
+    if (!getenv("REDTAIL_TC_NO_WLO_SKIP")) {
+        for (float v : w) {
+            const float c = v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v);
+            if (h2f(f2h(c)) != c) { wlo = true; break; }
+        }
+    } else wlo = true;
+    t->wlo = wlo;
+    p.nb1 = wlo ? 6 * kCoutPad : 3 * kCoutPad;
+    p.b_tile_bytes = p.nb1 * kCin * 2;
+    // Weight tiles [dh][dw][row][32 ch] fp16; rows: W_hi of filter planes v = 0, 1, 2 (32 rows each), then the W_lo rows.
+    std::vector<uint16_t> pk(static_cast<size_t>(9) * p.nb1 * kCin, 0);
+    for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s)
+            for (int v = 0; v < 3; ++v)
+                for (int k = 0; k < d.k; ++k)
+                    for (int c = 0; c < d.c; ++c) {
+                        float val = w[(((static_cast<size_t>(k) * 3 + v) * d.c + c) * 3 + r) * 3 + s];
+                        val = val > 65504.f ? 65504.f : (val < -65504.f ? -65504.f : val);
+                        const size_t tile = static_cast<size_t>(r * 3 + s) * p.nb1;
+                        const uint16_t hb = f2h(val);
+                        pk[(tile + v * kCoutPad + k) * kCin + c] = hb;
+                        if (wlo) pk[(tile + 3 * kCoutPad + v * kCoutPad + k) * kCin + c] = f2h((val - h2f(hb)) * 2048.f);
+                    }
+    if (cudaMalloc(&t->w_dev, pk.size() * 2) != cudaSuccess ||
+        cudaMemcpy(t->w_dev, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(t->w_dev);
+        delete t;
+        return static_cast<int>(cudaErrorMemoryAllocation);
+    }
+    {
+        const uint64_t dims[2] = {static_cast<uint64_t>(kCin), static_cast<uint64_t>(9) * p.nb1};
+        const uint64_t strides[1] = {static_cast<uint64_t>(kCin) * 2};
+        const uint32_t box[2] = {static_cast<uint32_t>(kCin), static_cast<uint32_t>(p.nb1)};
+        const int rc = make_tensor_map(&t->map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, t->w_dev, dims, strides, box, nullptr,
+                                       CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc != 0) { cudaFree(t->w_dev); delete t; return RT_ERR_UNSUPPORTED; }
+    }
+    t->smem_bytes = 9 * p.b_tile_bytes + kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers, bias*/;
+    if (t->smem_bytes < 120 * 1024) t->smem_bytes = 120 * 1024;      // one CTA per SM: the 512-column TMEM grab never contends
+    plan->ds = t;
+    return RT_OK;
+}
+
+void ds_plan_destroy(rt_conv3d_plan* plan) {
+    DsPlanImpl* t = static_cast<DsPlanImpl*>(plan->ds);
+    if (!t) return;
+    cudaFree(t->w_dev);
+    delete t;
+    plan->ds = nullptr;
+}
+
+int ds_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const void* x, void* y, cudaStream_t s) {
+    const DsPlanImpl* t = static_cast<const DsPlanImpl*>(plan->ds);
+    DsParams p = t->p;
+    p.njobs = p.tiles_per_sample * n;
+    if (p.njobs == 0) return RT_OK;
+    const __half* hi = static_cast<const __half*>(x);
+    const __half* lo = hi + t->in_elems;
+    CUtensorMap ma_hi, ma_lo;
+    {
+        const uint64_t dims[5] = {static_cast<uint64_t>(kCin), static_cast<uint64_t>(t->in_w), static_cast<uint64_t>(t->in_h),
+                                  static_cast<uint64_t>(t->in_d), static_cast<uint64_t>(n)};
+        const uint64_t st[4] = {static_cast<uint64_t>(kCin) * 2, static_cast<uint64_t>(kCin) * 2 * t->in_w,
+                                static_cast<uint64_t>(kCin) * 2 * t->in_w * t->in_h, static_cast<uint64_t>(t->in_elems) * 4};
+        const uint32_t box[5] = {static_cast<uint32_t>(kCin), static_cast<uint32_t>(kTw), static_cast<uint32_t>(kTh + 2), 1u, 1u};
+        int rc = make_tensor_map(&ma_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, hi, dims, st, box, nullptr, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc == 0) rc = make_tensor_map(&ma_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, lo, dims, st, box, nullptr, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc != 0) return rc > 0 ? rc : RT_ERR_UNSUPPORTED;
+    }
+    int grid = num_sms();
+    if (grid > p.njobs) grid = p.njobs;
+    static bool attr_set[2][64] = {};
+    int dev = 0;
+    RT_CUDA(cudaGetDevice(&dev));
+    const int wi = t->wlo ? 1 : 0;
+    if (dev < 0 || dev >= 64 || !attr_set[wi][dev]) {
+        if (t->wlo) RT_CUDA(cudaFuncSetAttribute(conv3d_ds_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        else RT_CUDA(cudaFuncSetAttribute(conv3d_ds_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        if (dev >= 0 && dev < 64) attr_set[wi][dev] = true;
+    }
+    if (t->wlo) conv3d_ds_kernel<true><<<grid, kThreads, t->smem_bytes, s>>>(ma_hi, ma_lo, t->map_w, p, plan->bias, static_cast<__half*>(y));
+    else conv3d_ds_kernel<false><<<grid, kThreads, t->smem_bytes, s>>>(ma_hi, ma_lo, t->map_w, p, plan->bias, static_cast<__half*>(y));
+    note_launch(t->wlo ? "conv3d_ds_fp16x2split" : "conv3d_ds_fp16x2split_w16");
+    RT_CHECK_LAUNCH();
+    return RT_OK;
+}
+
+}  // namespace rt

@@ -17,6 +17,11 @@ struct rt_conv3d_plan {
     int cout = 0, cin = 0;
     // ---- tcgen05 path (filled by rt::tc_plan_init when precision != RT_PREC_SIMT and the shape is supported).
     void* tc = nullptr;
+    // ---- depth-stationary tcgen05 kernel (conv3d_ds.cu): 32 -> 32 channel, 3x3x3, stride 1, split16 in/out; preferred over `tc`
+    //      when set (a launch with a skip tensor still takes the generic kernel).
+    void* ds = nullptr;
+    // ---- transposed conv (Cout = 1) + slice + soft-argmax/min as one kernel (deconv_softargmax.cu); set iff desc.fuse_softargmax.
+    void* dsa = nullptr;
 };
 
 namespace rt {
@@ -31,4 +36,14 @@ void tc_plan_destroy(rt_conv3d_plan* p);
 size_t tc_workspace_size(const rt_conv3d_plan* p, int max_batch);
 int tc_conv3d_enqueue(const rt_conv3d_plan* p, int n, const float* x, const float* skip, float* y, void* workspace,
                       cudaStream_t s);
+// Depth-stationary kernel (conv3d_ds.cu).  ds_plan_init returns RT_ERR_UNSUPPORTED (and leaves p->ds null) outside its shape class.
+bool ds_shape_supported(const rt_conv3d_desc& d);
+int ds_plan_init(rt_conv3d_plan* p, const std::vector<float>& w_kvcrs);
+void ds_plan_destroy(rt_conv3d_plan* p);
+int ds_conv3d_enqueue(const rt_conv3d_plan* p, int n, const void* x, void* y, cudaStream_t s);
+// Fused Conv3DTranspose(32 -> 1) + Slice + Softargmax (deconv_softargmax.cu); y = [n, Hx, Wx] fp32 disparities.
+bool dsa_shape_supported(const rt_conv3d_desc& d);
+int dsa_plan_init(rt_conv3d_plan* p, const std::vector<float>& w_kvcrs, const std::vector<float>& bias);
+void dsa_plan_destroy(rt_conv3d_plan* p);
+int dsa_enqueue(const rt_conv3d_plan* p, int n, const void* x, void* y, cudaStream_t s);
 }  // namespace rt

@@ -258,6 +258,8 @@ int rt_conv3d_create(const rt_conv3d_desc* d, rt_conv3d_plan** out) {
     if (d->transposed && (d->slice_d < 0 || d->slice_d >= d->out_dims[0])) return RT_ERR_ARG;
     if (!d->transposed && d->slice_d != 0) return RT_ERR_ARG;
     if (d->transposed && d->out_transposed) return RT_ERR_ARG;
+    if (d->fuse_softargmax < 0 || d->fuse_softargmax > 2) return RT_ERR_ARG;
+    if (d->fuse_softargmax && !dsa_shape_supported(*d)) return RT_ERR_UNSUPPORTED;     // one kernel covers the fused form
 
     rt_conv3d_plan* p = new rt_conv3d_plan();
     p->desc = *d;
@@ -298,22 +300,44 @@ int rt_conv3d_create(const rt_conv3d_desc* d, rt_conv3d_plan** out) {
         rt_conv3d_destroy(p);
         return RT_ERR_UNSUPPORTED;      // the CUDA-core validation kernels only speak the dense plugin layouts
     }
+    if (d->fuse_softargmax) {
+        const int rc = dsa_plan_init(p, w, b);
+        if (rc != RT_OK) {
+            rt_conv3d_destroy(p);
+            return rc;
+        }
+        *out = p;
+        return RT_OK;
+    }
     if (d->precision != RT_PREC_SIMT) {
         const int rc = tc_plan_init(p, w, b);
         if (rc != RT_OK) {           // no silent downgrade of a requested tensor-core precision
             rt_conv3d_destroy(p);
             return rc;
         }
+        if (ds_shape_supported(*d)) {
+            const int rc2 = ds_plan_init(p, w);
+            if (rc2 != RT_OK && rc2 != RT_ERR_UNSUPPORTED) {
+                rt_conv3d_destroy(p);
+                return rc2;
+            }
+        }
     }
     *out = p;
     return RT_OK;
 }
 
-int rt_conv3d_tc_supported(const rt_conv3d_desc* d) { return d && tc_shape_supported(*d) ? 1 : 0; }
+int rt_conv3d_tc_supported(const rt_conv3d_desc* d) {
+    if (!d) return 0;
+    if (d->fuse_softargmax) return dsa_shape_supported(*d) ? 1 : 0;     // the fused form has exactly one kernel
+    return tc_shape_supported(*d) ? 1 : 0;
+}
 
 void rt_conv3d_destroy(rt_conv3d_plan* p) {
     if (!p) return;
     tc_plan_destroy(p);
+    ds_plan_destroy(p);
+    dsa_plan_destroy(p);
     cudaFree(p->w_simt);
     cudaFree(p->bias);
     delete p;
@@ -328,6 +352,8 @@ int rt_conv3d_enqueue(const rt_conv3d_plan* p, int n, const void* x, const void*
                       void* stream) {
     if (!p || !x || !y || n < 0) return RT_ERR_ARG;
     if (n == 0) return RT_OK;
+    if (p->dsa) return skip ? RT_ERR_ARG : dsa_enqueue(p, n, x, y, as_stream(stream));
+    if (p->ds && !skip) return ds_conv3d_enqueue(p, n, x, y, as_stream(stream));
     if (p->tc)
         return tc_conv3d_enqueue(p, n, static_cast<const float*>(x), static_cast<const float*>(skip),
                                  static_cast<float*>(y), workspace, as_stream(stream));

@@ -111,6 +111,10 @@ struct TcParams {
                              // tcgen05.ld drains, 2 = no MMAs are issued, 4 = the producer moves no data, 8 = no output phase (bias/ELU/stores)
     int out_c;               // channels of the output tensor (split16 addressing)
     long long out_lo;        // split16: offset of the lo plane, in halves
+    int interleave;          // > 0 (experiment, REDTAIL_TC_INTERLEAVE=1): job index = tile * nclasses + class over the common tile
+                             // grid (grid_d x grid_th x grid_tw), so that the un-merged parity classes of a transposed conv, which
+                             // read the SAME input tile, run at the same time on different SMs and share it in L2
+    int grid_d, grid_th, grid_tw;
     ClassInfo cls[kMaxClasses];
 };
 
@@ -155,12 +159,24 @@ pack_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* 
 // ---------------------------------------------------------------------------------------------------------------
 // Main kernel.
 // ---------------------------------------------------------------------------------------------------------------
-struct JobCoord { int cls, n, d, h0, w0; };
+struct JobCoord { int cls, n, d, h0, w0; bool empty; };
 
 __device__ __forceinline__ JobCoord decode_job(const TcParams& p, int job) {
     JobCoord j;
     j.n = job / p.jobs_per_sample;
     int r = job - j.n * p.jobs_per_sample;
+    j.empty = false;
+    if (p.interleave) {
+        j.cls = r % p.nclasses;
+        r /= p.nclasses;
+        j.w0 = (r % p.grid_tw) * p.tw;
+        r /= p.grid_tw;
+        j.h0 = (r % p.grid_th) * (p.th * p.mt);
+        j.d = r / p.grid_th;
+        const ClassInfo& ci = p.cls[j.cls];
+        j.empty = j.d >= ci.dc || j.h0 >= ci.hc || j.w0 >= ci.wc;     // this class has no tile here (its lattice is one shorter)
+        return j;
+    }
     int c = 0;
     while (c + 1 < p.nclasses && r >= p.cls[c + 1].job_begin) ++c;
     j.cls = c;
@@ -262,6 +278,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             uint32_t phase = 0;
             for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
                 const JobCoord jc = decode_job(p, job);
+                if (jc.empty) continue;
                 const ClassInfo& ci = p.cls[jc.cls];
                 for (int t = 0; t < ci.ntaps; ++t) {
                     const TapEntry te = ci.taps[t];
@@ -322,7 +339,11 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 const uint32_t st_lo0 = st_lo, stage16 = stage_bytes >> 4, a16 = a_bytes >> 4;
                 for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
                     int cls = 0;
-                    {
+                    if (p.interleave) {
+                        const JobCoord jc = decode_job(p, job);
+                        if (jc.empty) continue;
+                        cls = jc.cls;
+                    } else {
                         const int r = job % p.jobs_per_sample;
                         while (cls + 1 < p.nclasses && r >= p.cls[cls + 1].job_begin) ++cls;
                     }
@@ -381,6 +402,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             } else if (mw == 0)                          // sub-stage chunks (short chains on request): one issuing warp
             for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
                 const JobCoord jc = decode_job(p, job);
+                if (jc.empty) continue;
                 const int nkb = p.cls[jc.cls].ntaps * ncb;
                 // A chunk (one TMEM accumulation chain) is closed after `chunk_rows` filter rows inside a stage when chains
                 // are shorter than a stage, else after `chunk_kb` whole stages; the epilogue walks the same sequence.
@@ -458,6 +480,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         const int chunk_kb = p.chunk_kb, chunk_rows = p.chunk_rows;
         for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
             const JobCoord jc = decode_job(p, job);
+            if (jc.empty) continue;
             const ClassInfo& ci = p.cls[jc.cls];
             const int nkb = ci.ntaps * p.ncb;
             float acc0[MT][CPH];
@@ -869,6 +892,20 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
                         }
             }
     p.jobs_per_sample = job;
+    p.interleave = 0;
+    // Measured (round 2, NVSmall): deconv3D_2 0.530 -> 0.580 ms, deconv3D_1 0.193 -> 0.222 ms WITH the interleaved order, i.e. the
+    // input re-read is not what bounds these layers and neighbouring classes writing the same output lines from different SMs
+    // costs more than the L2 hits save.  Kept as an experiment switch (REDTAIL_TC_INTERLEAVE=1), off by default.
+    if (p.nclasses > 1 && getenv("REDTAIL_TC_INTERLEAVE") && atoi(getenv("REDTAIL_TC_INTERLEAVE")) == 1) {
+        p.grid_d = p.grid_th = p.grid_tw = 0;
+        for (int c2 = 0; c2 < p.nclasses; ++c2) {
+            p.grid_d = p.cls[c2].dc > p.grid_d ? p.cls[c2].dc : p.grid_d;
+            p.grid_th = p.cls[c2].tiles_h > p.grid_th ? p.cls[c2].tiles_h : p.grid_th;
+            p.grid_tw = p.cls[c2].tiles_w > p.grid_tw ? p.cls[c2].tiles_w : p.grid_tw;
+        }
+        p.interleave = 1;
+        p.jobs_per_sample = p.nclasses * p.grid_d * p.grid_th * p.grid_tw;
+    }
     for (int ci = 0; ci < p.nclasses; ++ci) {
         unsigned long long pack = 0;
         for (int t2 = 0; t2 < p.cls[ci].ntaps; ++t2) pack |= static_cast<unsigned long long>(p.cls[ci].taps[t2].nr & 3u) << (2 * t2);

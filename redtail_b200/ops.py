@@ -187,7 +187,7 @@ class Conv3d:
 
     def __init__(self, weights, bias, stride, pad_start, in_dims, out_dims=None, transposed=False,
                  precision=PREC_FP32, fuse_elu=False, out_transposed=False, slice_d=0,
-                 in_layout=LAYOUT_DENSE, out_layout=LAYOUT_DENSE, pad_end_d=0):
+                 in_layout=LAYOUT_DENSE, out_layout=LAYOUT_DENSE, pad_end_d=0, fuse_softargmax=0):
         w = np.ascontiguousarray(weights)
         assert w.ndim == 5 and w.dtype in (np.float32, np.float16)
         b = None if bias is None else np.ascontiguousarray(bias).astype(w.dtype)
@@ -212,6 +212,7 @@ class Conv3d:
         d.out_transposed = int(out_transposed)
         d.slice_d = int(slice_d)
         d.in_layout, d.out_layout, d.pad_end_d = int(in_layout), int(out_layout), int(pad_end_d)
+        d.fuse_softargmax = int(fuse_softargmax)     # transposed, one output channel: 1 soft-argmin / 2 soft-argmax -> y [N,Hx,Wx]
         self.desc = d
         self.transposed = transposed
         self.out_dims = tuple(out_dims)
@@ -238,7 +239,9 @@ class Conv3d:
                 shape = (n, 2, od[1], od[2], od[3], od[0])
             y = torch.empty(shape, dtype=torch.float16, device=x.device)
         else:
-            if self.transposed:
+            if self.desc.fuse_softargmax:
+                shape = (n, od[2], od[3])
+            elif self.transposed:
                 shape = (n, od[0] - self.desc.slice_d, od[1], od[2], od[3])
             elif self.desc.out_transposed:
                 shape = (n, od[1], od[0], od[2], od[3])

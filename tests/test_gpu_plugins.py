@@ -378,6 +378,32 @@ def test_conv3d_split16_chain(R, cin, cout, stride):
     check(y, ref, 2e-4)
 
 
+@pytest.mark.parametrize("cout,d,h,w_,n,wdtype", [(32, 6, 19, 37, 1, np.float32), (32, 3, 8, 16, 2, np.float32), (24, 4, 9, 50, 1, np.float32),
+                                                   (32, 5, 21, 33, 1, np.float16), (32, 2, 30, 17, 1, np.float32)])
+def test_conv3d_depth_stationary(R, monkeypatch, cout, d, h, w_, n, wdtype):
+    """32 -> <=32 channel 3x3x3 stride-1 convs in split16 run on the depth-stationary tcgen05 kernel (conv3d_ds.cu): against the
+    oracle, and bit for bit against the generic kernel forced to the same accumulation chunks (one chunk per filter plane and
+    column) -- both kernels add the same products in the same order."""
+    g = torch.Generator().manual_seed(cout + d + 5 * h)
+    x = torch.randn(n, d, 32, h, w_, generator=g)
+    w = (torch.randn(cout, 3, 32, 3, 3, generator=g) * (1.0 / np.sqrt(27 * 32)))
+    b = torch.randn(cout, generator=g)
+    if wdtype == np.float16:
+        w, b = w.half().float(), b.half().float()
+    ref = O.elu(O.transform(O.conv3d(x.double(), w.double(), b.double(), (1, 1, 1), (1, 1, 1)))).float()
+    xs = R.dense_to_split16(x.cuda())
+    mk = lambda: R.Conv3d(w.numpy(), b.numpy(), (1, 1, 1), (1, 1, 1), tuple(x.shape[1:]), precision=R.PREC_FP32, fuse_elu=True,
+                          in_layout=R.LAYOUT_SPLIT16, out_layout=R.LAYOUT_SPLIT16)
+    ys = mk()(xs)
+    assert R.last_kernel() == ("conv3d_ds_fp16x2split_w16" if wdtype == np.float16 else "conv3d_ds_fp16x2split"), R.last_kernel()
+    check(R.split16_to_dense(ys), ref, 2e-4)
+    monkeypatch.setenv("REDTAIL_TC_DS", "0")
+    monkeypatch.setenv("REDTAIL_TC_CHAIN", "6")
+    yg = mk()(xs)
+    assert "umma" in R.last_kernel(), R.last_kernel()
+    assert torch.equal(ys, yg), float((R.split16_to_dense(ys) - R.split16_to_dense(yg)).abs().max())
+
+
 def test_conv3d_transpose_split16_skip(R):
     g = torch.Generator().manual_seed(77)
     y = torch.randn(1, 64, 4, 9, 17, generator=g)
@@ -391,6 +417,27 @@ def test_conv3d_transpose_split16_skip(R):
     yin = R.dense_to_split16(y.permute(0, 2, 1, 3, 4).contiguous().cuda())     # [N,D,K,H,W] -> split16 [D][H][W][K]
     out = R.split16_to_dense(op(yin, R.dense_to_split16(skip.cuda())))
     check(out, ref, 3e-4)
+
+
+@pytest.mark.parametrize("d,h,w_,n,slice_d,is_min,wdtype", [(6, 9, 17, 1, 1, True, np.float32), (4, 21, 40, 2, 1, True, np.float32),
+                                                            (5, 8, 16, 1, 0, False, np.float32), (7, 13, 33, 1, 1, True, np.float16)])
+def test_deconv_softargmax_fused(R, d, h, w_, n, slice_d, is_min, wdtype):
+    """Conv3DTranspose (32 -> 1, stride 2) + Slice + Softargmax as one kernel (deconv_softargmax.cu) against the oracle's three ops."""
+    g = torch.Generator().manual_seed(d * 100 + h)
+    y = torch.randn(n, 32, d, h, w_, generator=g)
+    w = torch.randn(32, 3, 1, 3, 3, generator=g) * 0.25
+    b = torch.randn(1, generator=g)
+    if wdtype == np.float16:
+        w, b = w.half().float(), b.half().float()
+    od = (2 * d + 1, 1, 2 * h - 1, 2 * w_ - 1)
+    vol = O.slice_d(O.conv3d_transpose(y.double(), w.double(), b.double(), (2, 2, 2), (0, 1, 1), od), 0, od[0] - slice_d)
+    ref = O.softargmax(vol[:, :, 0], is_min).float()
+    op = R.Conv3d(w.numpy(), b.numpy(), (2, 2, 2), (0, 1, 1), (32, d, h, w_), out_dims=od, transposed=True, precision=R.PREC_FP32,
+                  slice_d=slice_d, in_layout=R.LAYOUT_SPLIT16, fuse_softargmax=1 if is_min else 2)
+    yin = R.dense_to_split16(y.permute(0, 2, 1, 3, 4).contiguous().cuda())
+    out = op(yin)
+    assert R.last_kernel().startswith("deconv_softargmax"), R.last_kernel()
+    check(out, ref.reshape(out.shape), 2e-4)
 
 
 # ---- fused CostVolume -> Conv3D (the volume is never built): same values as the unfused plugin pair ----
