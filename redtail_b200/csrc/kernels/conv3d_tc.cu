@@ -483,6 +483,28 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             if (jc.empty) continue;
             const ClassInfo& ci = p.cls[jc.cls];
             const int nkb = ci.ntaps * p.ncb;
+            // The skip tensor is read once, long after this point: ask L2 for this tile's lines now so that the output phase
+            // does not wait for HBM (split16 outputs only; the transposed convs of the decoder are the layers with a skip).
+            if (skip != nullptr && p.out_split) {
+                const __half* sk16 = reinterpret_cast<const __half*>(skip);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int hi_ = jc.h0 + mt * p.th + hl, wi_ = jc.w0 + wl;
+                    if (hi_ < ci.hc && wi_ < ci.wc) {
+                        const int bd = jc.d * p.out_s[0] + ci.ed, bh = hi_ * p.out_s[1] + ci.eh, bw = wi_ * p.out_s[2] + ci.ew;
+                        const long long rowbase = jc.n * p.out_sn + ((static_cast<long long>(bd) * p.out_h + bh) * p.out_w + bw) * p.out_c;
+#pragma unroll
+                        for (int k0 = 0; k0 < CPH; k0 += 8) {
+                            const ColInfo c0 = s_col[col0 + k0];
+                            const int q8 = c0.pidx;
+                            if (q8 < 8 && bd + (q8 >> 2) < p.out_d && bh + ((q8 >> 1) & 1) < p.out_h && bw + (q8 & 1) < p.out_w) {
+                                prefetch_l2(sk16 + rowbase + c0.off);
+                                prefetch_l2(sk16 + p.out_lo + rowbase + c0.off);
+                            }
+                        }
+                    }
+                }
+            }
             float acc0[MT][CPH];
             float acc1[MT][SPLIT ? CPH : 1];
 #pragma unroll
@@ -561,6 +583,20 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     // (guaranteed by the column order chosen on the host) -> one 16-byte store per fp16 plane.
                     __half* oh16 = reinterpret_cast<__half*>(out);
                     const __half* sk16 = reinterpret_cast<const __half*>(skip);
+                    // every skip vector of this row first (the accumulators' D1 half is dead here, registers are free): one
+                    // exposed memory latency per tile instead of one per batch of 8 columns
+                    constexpr bool kUpFront = CPH <= 32;          // 64 columns per thread: the vectors would not fit in registers
+                    uint4 sh[kUpFront ? CPH / 8 : 1], sl[kUpFront ? CPH / 8 : 1];
+                    if (skip && kUpFront) {
+#pragma unroll
+                        for (int k0 = 0; k0 < CPH; k0 += 8) {
+                            const ColInfo c0 = s_col[col0 + k0];
+                            if ((vmask >> c0.pidx) & 1u) {
+                                sh[k0 / 8] = __ldg(reinterpret_cast<const uint4*>(sk16 + rowbase + c0.off));
+                                sl[k0 / 8] = __ldg(reinterpret_cast<const uint4*>(sk16 + p.out_lo + rowbase + c0.off));
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int k0 = 0; k0 < CPH; k0 += 8) {
                         const ColInfo c0 = s_col[col0 + k0];
@@ -572,10 +608,12 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                                 v[j] = acc0[mt][k0 + j] + s_bias[c0.ch + j];
                             }
                             if (skip) {
-                                const uint4 sh = __ldg(reinterpret_cast<const uint4*>(sk16 + idx));
-                                const uint4 sl = __ldg(reinterpret_cast<const uint4*>(sk16 + p.out_lo + idx));
-                                const __half* hh = reinterpret_cast<const __half*>(&sh);
-                                const __half* ll = reinterpret_cast<const __half*>(&sl);
+                                if (!kUpFront) {
+                                    sh[0] = __ldg(reinterpret_cast<const uint4*>(sk16 + idx));
+                                    sl[0] = __ldg(reinterpret_cast<const uint4*>(sk16 + p.out_lo + idx));
+                                }
+                                const __half* hh = reinterpret_cast<const __half*>(&sh[kUpFront ? k0 / 8 : 0]);
+                                const __half* ll = reinterpret_cast<const __half*>(&sl[kUpFront ? k0 / 8 : 0]);
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[j] += fmaf(__half2float(ll[j]), 1.f / 2048.f, __half2float(hh[j]));
                             }
