@@ -240,6 +240,50 @@ protected:
     virtual ~IActivationLayer() {}
 };
 
+enum class PoolingType : int { kMAX = 0, kAVERAGE = 1, kMAX_AVERAGE_BLEND = 2 };
+template <> inline int EnumMax<PoolingType>() { return 3; }
+
+// The TrailNet classifier (models/pretrained/TrailNet_SResNet-18.prototxt, run by ros/packages/caffe_ros/src/tensor_net.cpp
+// through the Caffe parser) needs three more native layers: pooling, fully connected, soft-max.
+class IPoolingLayer : public ILayer {
+public:
+    virtual void setPoolingType(PoolingType type) = 0;
+    virtual PoolingType getPoolingType() const = 0;
+    virtual void setWindowSize(DimsHW windowSize) = 0;
+    virtual DimsHW getWindowSize() const = 0;
+    virtual void setStride(DimsHW stride) = 0;
+    virtual DimsHW getStride() const = 0;
+    virtual void setPadding(DimsHW padding) = 0;
+    virtual DimsHW getPadding() const = 0;
+protected:
+    virtual ~IPoolingLayer() {}
+};
+
+class IFullyConnectedLayer : public ILayer {
+public:
+    virtual void setNbOutputChannels(int nbOutputs) = 0;
+    virtual int getNbOutputChannels() const = 0;
+    virtual void setKernelWeights(Weights weights) = 0;
+    virtual Weights getKernelWeights() const = 0;
+    virtual void setBiasWeights(Weights weights) = 0;
+    virtual Weights getBiasWeights() const = 0;
+protected:
+    virtual ~IFullyConnectedLayer() {}
+};
+
+class ISoftMaxLayer : public ILayer {      // over the channel dimension of a CHW tensor
+protected:
+    virtual ~ISoftMaxLayer() {}
+};
+
+// Output extent of a pooling layer; the Caffe parser installs Caffe's rounding (ceil, last window must start inside the image).
+class IOutputDimensionsFormula {
+public:
+    virtual DimsHW compute(DimsHW inputDims, DimsHW kernelSize, DimsHW stride, DimsHW padding, DimsHW dilation, const char* layerName) const = 0;
+protected:
+    virtual ~IOutputDimensionsFormula() {}
+};
+
 class IShuffleLayer : public ILayer {
 public:
     virtual void setReshapeDimensions(Dims dimensions) = 0;
@@ -313,6 +357,11 @@ public:
     virtual int getNbOutputs() const = 0;
     virtual ITensor* getOutput(int index) const = 0;
     virtual void destroy() = 0;
+    virtual IPoolingLayer* addPooling(ITensor& input, PoolingType type, DimsHW windowSize) = 0;
+    virtual IFullyConnectedLayer* addFullyConnected(ITensor& input, int nbOutputs, Weights kernelWeights, Weights biasWeights) = 0;
+    virtual ISoftMaxLayer* addSoftMax(ITensor& input) = 0;
+    virtual void setPoolingOutputDimensionsFormula(IOutputDimensionsFormula* formula) = 0;   // nullptr: floor ((in + 2 pad - k) / stride) + 1
+    virtual IOutputDimensionsFormula& getPoolingOutputDimensionsFormula() const = 0;
 protected:
     virtual ~INetworkDefinition() {}
 };

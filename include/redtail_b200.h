@@ -176,6 +176,23 @@ void rt_conv2d_destroy(rt_conv2d_plan* plan);
 void rt_conv2d_out_dims(const rt_conv2d_plan* plan, int* out_h, int* out_w);
 int  rt_conv2d_enqueue(const rt_conv2d_plan* plan, int n, const void* x, void* y, void* stream);
 
+/* ---- non-convolution layers of the TrailNet classifier (models/pretrained/TrailNet_SResNet-18.prototxt; ------------------
+ *      ros/packages/caffe_ros/src/tensor_net.cpp runs it through TensorRT's Caffe parser).  Dense fp32 NCHW tensors. ------ */
+/* y = x * scale[c] + shift[c]  (Caffe Scale layer with bias_term; a NULL array means 1 / 0).  x [n,c,hw]. */
+int rt_scale_channel(const void* x, void* y, int n, int c, int64_t hw, const float* scale, const float* shift, void* stream);
+/* S-ReLU chain of the model (prototxt:54-105): y = max(x * s1[c] + b1[c], 0) * s2[c] + b2[c] in one pass. */
+int rt_srelu(const void* x, void* y, int n, int c, int64_t hw, const float* s1, const float* b1, const float* s2, const float* b2,
+             void* stream);
+int rt_relu(const void* x, void* y, int64_t count, void* stream);
+/* Caffe pooling: out_h/out_w as the caller computed them (Caffe: ceil((in + 2 pad - k) / stride) + 1, last window starting
+ * inside the image), windows clipped at the border; AVE divides by the window area clipped to the PADDED image. */
+int rt_pool2d(const void* x, void* y, int n, int c, int h, int w, int out_h, int out_w, int k, int stride, int pad, int is_max,
+              void* stream);
+/* InnerProduct: y[n,m] = b[m] + sum_k x[n,k] W[m,k]  (W, b device fp32; b may be NULL). */
+int rt_fully_connected(const void* x, const float* w, const float* b, void* y, int n, int k, int m, void* stream);
+/* Softmax over the channel dimension of [n,c,inner], max-subtracted. */
+int rt_softmax_channels(const void* x, void* y, int n, int c, int64_t inner, void* stream);
+
 /* ---- image side of the apps (sample_app/main.cpp:83-98 readImgFile, :317-330 PNG output) -------------- */
 /* src: n 8-bit BGR images [src_h, src_w, 3] (row pitch src_pitch bytes, images src_pitch*src_h apart), device memory
  * -> dst [n,3,dst_h,dst_w] fp32 RGB in [0,1]: float conversion, cv::resize INTER_AREA (down-scaling or identity only),

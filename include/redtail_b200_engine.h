@@ -57,6 +57,30 @@ int rt_stereo_num_layers(const rt_stereo_engine* engine);
 size_t rt_stereo_device_bytes(const rt_stereo_engine* engine);
 const char* rt_stereo_last_error(void);
 
+/* ---- single-input classifier networks from Caffe models (TrailNet S-ResNet-18) ------------------------------------------
+ * What ros/packages/caffe_ros/src/tensor_net.cpp does in C++ (loadNetwork :182-260: Caffe parser -> buildCudaEngine ->
+ * serialize -> deserializeCudaEngine -> context; forward :262-291: cudaMemcpy in, execute) as plain C entry points.  The
+ * model goes through the nvcaffeparser1-compatible parser of include/NvCaffeParser.h. */
+typedef struct rt_net_engine rt_net_engine;
+/* output_blob is marked as the network output (tensor_net.cpp:144-151).  fp16 = 1: convolutions in the fp16 configuration. */
+int rt_caffe_create(const char* prototxt_path, const char* caffemodel_path, const char* input_blob, const char* output_blob,
+                    int max_batch, rt_net_engine** engine);
+void rt_net_destroy(rt_net_engine* engine);
+/* CHW of the input and output bindings (tensor_net.cpp:231-247). */
+int rt_net_dims(const rt_net_engine* engine, int in_chw[3], int out_chw[3]);
+/* Device buffers in [batch,C,H,W], out [batch,Co,Ho,Wo] fp32; asynchronous on `stream`. */
+int rt_net_enqueue(rt_net_engine* engine, int batch, const float* in, float* out, void* stream);
+/* Host buffers: H2D copy, inference, D2H copy, synchronous (TensorNet::forward without the OpenCV preprocessing). */
+int rt_net_execute_host(rt_net_engine* engine, int batch, const float* in, float* out);
+/* One profiled execution: "name\tms\n" per executed step. */
+int rt_net_profile(rt_net_engine* engine, int batch, const float* in, float* out, char* buf, size_t buf_len);
+/* Engine plan (tensor_net.cpp:168-172, 196-217: the model cache file). */
+size_t rt_net_serialize(const rt_net_engine* engine, void* buf, size_t buf_len);
+int rt_net_deserialize(const void* plan, size_t plan_size, int max_batch, rt_net_engine** engine);
+int rt_net_num_layers(const rt_net_engine* engine);
+/* HOST ONLY (no CUDA device needed): the plan rt_net_serialize would write for this model, without building an engine. */
+size_t rt_caffe_dump_plan(const char* prototxt_path, const char* caffemodel_path, const char* output_blob, int max_batch, void* buf, size_t buf_len);
+
 #ifdef __cplusplus
 }
 #endif

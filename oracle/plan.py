@@ -23,7 +23,7 @@ from . import ops
 
 MAGIC = b"RTB2PLAN"
 MAX_DIMS = 8
-K_CONV, K_DECONV, K_SCALE, K_ELTWISE, K_CONCAT, K_ACTIVATION, K_SHUFFLE, K_PLUGIN = range(8)
+K_CONV, K_DECONV, K_SCALE, K_ELTWISE, K_CONCAT, K_ACTIVATION, K_SHUFFLE, K_PLUGIN, K_POOLING, K_FC, K_SOFTMAX = range(11)
 P_ELU, P_COSTVOL, P_SOFTARGMAX, P_CONV3D, P_CONV3D_T, P_TRANSFORM, P_PADDING, P_SLICE = range(8)
 
 
@@ -102,6 +102,13 @@ def parse(buf, round_fp16=False):
             r.align8()
             L["plugin"] = _parse_plugin(buf[r.p:r.p + n], round_fp16)
             r.p += n
+        elif k == K_POOLING:       # the Caffe-model layers (TrailNet): pooling type, window, stride, pad, output extent
+            L["pool"], L["k"], L["stride"], L["pad"], L["oh"], L["ow"] = r.get("i"), r.get("i"), r.get("i"), r.get("i"), r.get("i"), r.get("i")
+        elif k == K_FC:
+            L["maps"] = r.get("i")
+            L["w"], L["b"] = r.weights(), r.weights()
+        elif k == K_SOFTMAX:
+            pass
         else:
             assert k == K_CONCAT, k
         layers.append(L)
@@ -213,13 +220,32 @@ def execute(plan, feeds, dtype=torch.float64):
                 cin = x[0].shape[1]
                 w = T(L["w"]).view(cin, L["maps"], *L["ksize"])
                 y = ops.deconv2d(x[0], w, T(L["b"]), L["stride"], L["pad"])
+            elif k == K_SCALE and L["mode"] == 1:          # per channel (Caffe Scale layer): x * scale[c] + shift[c]
+                assert L["power"] is None
+                y = x[0]
+                if L["scale"] is not None:
+                    y = y * T(L["scale"]).view(1, -1, 1, 1)
+                if L["shift"] is not None:
+                    y = y + T(L["shift"]).view(1, -1, 1, 1)
             elif k == K_SCALE:
                 assert L["mode"] == 0
                 s = lambda a, dflt: float(a[0]) if a is not None else dflt
                 y = ops.scale(x[0], s(L["shift"], 0.0), s(L["scale"], 1.0), s(L["power"], 1.0))
             elif k == K_ACTIVATION:
-                assert L["act"] == 1, "only kSIGMOID is used by the builders"
-                y = ops.sigmoid(x[0])
+                assert L["act"] in (0, 1), "kRELU (Caffe models) / kSIGMOID (stereo builders)"
+                y = torch.relu(x[0]) if L["act"] == 0 else ops.sigmoid(x[0])
+            elif k == K_POOLING:
+                from . import caffe
+                y = torch.from_numpy(caffe._pool(x[0].numpy(), "MAX" if L["pool"] == 0 else "AVE", L["k"], L["stride"], L["pad"]))
+                assert tuple(y.shape[2:]) == (L["oh"], L["ow"]), (y.shape, L["oh"], L["ow"])
+            elif k == K_FC:
+                x2 = x[0].reshape(x[0].shape[0], -1)
+                y = x2 @ T(L["w"]).view(L["maps"], -1).t()
+                if L["b"] is not None:
+                    y = y + T(L["b"]).view(1, -1)
+                y = y.view(y.shape[0], -1, 1, 1)
+            elif k == K_SOFTMAX:
+                y = torch.softmax(x[0], dim=1)
             elif k == K_ELTWISE:
                 assert L["op"] == 0
                 y = x[0] + x[1]

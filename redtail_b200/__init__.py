@@ -10,6 +10,6 @@ a GPU (so symbols can be inspected), every compute call fails loudly without one
 """
 from ._lib import kernels_lib, engine_lib, lib_paths, LibraryMissing  # noqa: F401
 from . import ops  # noqa: F401
-from .engine import StereoEngine  # noqa: F401
+from .engine import StereoEngine, CaffeNet  # noqa: F401
 
-__all__ = ["ops", "StereoEngine", "kernels_lib", "engine_lib", "lib_paths", "LibraryMissing"]
+__all__ = ["ops", "StereoEngine", "CaffeNet", "kernels_lib", "engine_lib", "lib_paths", "LibraryMissing"]

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBDIR = os.path.join(HERE, "lib")
+LIBDIR = os.environ.get("REDTAIL_LIB_DIR") or os.path.join(HERE, "lib")     # REDTAIL_LIB_DIR: A/B builds (tools/)
 
 
 class LibraryMissing(RuntimeError):
@@ -47,6 +47,12 @@ KERNEL_API = {
     "rt_disparity_to_u16": (_I, [_P, _P, _L, _F, _P]),
     "rt_write_png16": (_I, [C.c_char_p, _P, _I, _I]),
     "rt_last_kernel": (C.c_char_p, []),
+    "rt_scale_channel": (_I, [_P, _P, _I, _I, _L, _P, _P, _P]),
+    "rt_srelu": (_I, [_P, _P, _I, _I, _L, _P, _P, _P, _P, _P]),
+    "rt_relu": (_I, [_P, _P, _L, _P]),
+    "rt_pool2d": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "rt_fully_connected": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "rt_softmax_channels": (_I, [_P, _P, _I, _I, _L, _P]),
     "rt_cost_volume": (_I, [_I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rt_corr_cost_volume": (_I, [_I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rt_elu": (_I, [_I, _P, _P, _L, _P]),
@@ -92,6 +98,16 @@ ENGINE_API = {
     "rt_stereo_num_layers": (_I, [_P]),
     "rt_stereo_device_bytes": (C.c_size_t, [_P]),
     "rt_stereo_last_error": (C.c_char_p, []),
+    "rt_caffe_create": (_I, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _I, C.POINTER(_P)]),
+    "rt_net_destroy": (None, [_P]),
+    "rt_net_dims": (_I, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "rt_net_enqueue": (_I, [_P, _I, _P, _P, _P]),
+    "rt_net_execute_host": (_I, [_P, _I, _P, _P]),
+    "rt_net_profile": (_I, [_P, _I, _P, _P, C.c_char_p, C.c_size_t]),
+    "rt_net_serialize": (C.c_size_t, [_P, _P, C.c_size_t]),
+    "rt_net_deserialize": (_I, [_P, C.c_size_t, _I, C.POINTER(_P)]),
+    "rt_net_num_layers": (_I, [_P]),
+    "rt_caffe_dump_plan": (C.c_size_t, [C.c_char_p, C.c_char_p, C.c_char_p, _I, _P, C.c_size_t]),
     # nvinfer1 shim factories (C linkage, include/NvInfer.h)
     "createInferBuilder_INTERNAL": (_P, [_P, _I]),
     "createInferRuntime_INTERNAL": (_P, [_P, _I]),

@@ -13,7 +13,9 @@
 #include <cuda_runtime_api.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -123,7 +125,7 @@ struct TensorImpl : public ITensor {
     bool isNetworkOutput() const override { return is_output; }
 };
 
-enum class LKind { kConv, kDeconv, kScale, kEltwise, kConcat, kActivation, kShuffle, kPlugin };
+enum class LKind { kConv, kDeconv, kScale, kEltwise, kConcat, kActivation, kShuffle, kPlugin, kPooling, kFullyConnected, kSoftMax };
 
 struct LayerData {
     LKind kind;
@@ -141,6 +143,8 @@ struct LayerData {
     bool has_reshape = false;
     IPlugin* plugin = nullptr;
     IPluginExt* plugin_ext = nullptr;
+    PoolingType pool = PoolingType::kMAX;
+    int pool_oh = 0, pool_ow = 0;      // output extent fixed by a plan (the formula object is not serialisable); 0 = use the formula
 };
 
 struct LayerNode {
@@ -187,6 +191,32 @@ struct ShuffleLayer : public LayerT<IShuffleLayer> {
     Dims getReshapeDimensions() const override { return d.reshape; }
 };
 struct PluginLayer : public LayerT<IPluginLayer> { IPlugin& getPlugin() override { return *d.plugin; } };
+struct PoolingLayer : public LayerT<IPoolingLayer> {
+    void setPoolingType(PoolingType t) override { d.pool = t; }
+    PoolingType getPoolingType() const override { return d.pool; }
+    void setWindowSize(DimsHW k) override { d.ksize = k; }
+    DimsHW getWindowSize() const override { return d.ksize; }
+    void setStride(DimsHW s) override { d.stride = s; }
+    DimsHW getStride() const override { return d.stride; }
+    void setPadding(DimsHW p) override { d.pad = p; }
+    DimsHW getPadding() const override { return d.pad; }
+};
+struct FullyConnectedLayer : public LayerT<IFullyConnectedLayer> {
+    void setNbOutputChannels(int n) override { d.nb_out_maps = n; }
+    int getNbOutputChannels() const override { return d.nb_out_maps; }
+    void setKernelWeights(Weights w) override { d.kw = w; }
+    Weights getKernelWeights() const override { return d.kw; }
+    void setBiasWeights(Weights w) override { d.bw = w; }
+    Weights getBiasWeights() const override { return d.bw; }
+};
+struct SoftMaxLayer : public LayerT<ISoftMaxLayer> {};
+// TensorRT's default pooling extent: floor((in + 2 pad - k) / stride) + 1.
+struct FloorPoolingFormula : public IOutputDimensionsFormula {
+    DimsHW compute(DimsHW in, DimsHW k, DimsHW stride, DimsHW pad, DimsHW, const char*) const override
+    {
+        return DimsHW((in.h() + 2 * pad.h() - k.h()) / stride.h() + 1, (in.w() + 2 * pad.w() - k.w()) / stride.w() + 1);
+    }
+};
 
 class NetworkImpl : public INetworkDefinition {
 public:
@@ -260,6 +290,24 @@ public:
         l->d.plugin = &plugin; l->d.plugin_ext = &plugin;
         return l;
     }
+    IPoolingLayer* addPooling(ITensor& input, PoolingType type, DimsHW windowSize) override
+    {
+        auto* l = add<PoolingLayer>(LKind::kPooling, LayerType::kPOOLING, {&input}, 1);
+        l->d.pool = type; l->d.ksize = windowSize; l->d.stride = DimsHW(1, 1); l->d.pad = DimsHW(0, 0);
+        return l;
+    }
+    IFullyConnectedLayer* addFullyConnected(ITensor& input, int nbOutputs, Weights kw, Weights bw) override
+    {
+        auto* l = add<FullyConnectedLayer>(LKind::kFullyConnected, LayerType::kFULLY_CONNECTED, {&input}, 1);
+        l->d.nb_out_maps = nbOutputs; l->d.kw = kw; l->d.bw = bw;
+        return l;
+    }
+    ISoftMaxLayer* addSoftMax(ITensor& input) override { return add<SoftMaxLayer>(LKind::kSoftMax, LayerType::kSOFTMAX, {&input}, 1); }
+    void setPoolingOutputDimensionsFormula(IOutputDimensionsFormula* f) override { pool_formula_ = f; invalidate(); }
+    IOutputDimensionsFormula& getPoolingOutputDimensionsFormula() const override
+    {
+        return pool_formula_ ? *pool_formula_ : const_cast<FloorPoolingFormula&>(floor_formula_);
+    }
     int getNbLayers() const override { return static_cast<int>(layers_.size()); }
     ILayer* getLayer(int i) const override { return i >= 0 && i < getNbLayers() ? layers_[i]->iface() : nullptr; }
     int getNbInputs() const override { return static_cast<int>(inputs_.size()); }
@@ -278,9 +326,17 @@ public:
         return true;
     }
     // A layer's parameters (stride / padding / reshape) may be set after add*(): force re-resolution before build.
-    void invalidate() { resolved_ = 0; }
+    void invalidate()
+    {
+        resolved_ = 0;
+        if (!pool_from_plan_)
+            for (auto& l : layers_) if (l->d.kind == LKind::kPooling) { l->d.pool_oh = 0; l->d.pool_ow = 0; }
+    }
+    bool pool_from_plan_ = false;       // deserialised networks carry the pooling extents the original formula produced
 
     ILogger& log_;
+    IOutputDimensionsFormula* pool_formula_ = nullptr;
+    FloorPoolingFormula floor_formula_;
     std::vector<std::unique_ptr<TensorImpl>> tensors_;
     std::vector<std::unique_ptr<LayerNode>> layers_;
     std::vector<TensorImpl*> inputs_, outputs_;
@@ -339,7 +395,32 @@ private:
                 break;
             }
             case LKind::kScale:
-                if (d.smode != ScaleMode::kUNIFORM) return fail(d, "only ScaleMode::kUNIFORM is supported");
+                if (d.smode == ScaleMode::kCHANNEL) {
+                    if (in0.nbDims != 3) return fail(d, "per-channel scale expects a CHW input");
+                    for (const Weights* w : {&d.shift, &d.scale, &d.power})
+                        if (w->count != 0 && w->count != in0.d[0]) return fail(d, "per-channel scale: weight count != channels");
+                } else if (d.smode != ScaleMode::kUNIFORM) return fail(d, "ScaleMode::kELEMENTWISE is not supported");
+                d.out[0]->dims = in0;
+                break;
+            case LKind::kPooling: {
+                if (in0.nbDims != 3) return fail(d, "pooling expects a CHW input");
+                if (d.pool == PoolingType::kMAX_AVERAGE_BLEND) return fail(d, "PoolingType::kMAX_AVERAGE_BLEND is not supported");
+                if (d.ksize.h() != d.ksize.w() || d.stride.h() != d.stride.w() || d.pad.h() != d.pad.w()) return fail(d, "pooling: square windows only");
+                DimsHW o(d.pool_oh, d.pool_ow);
+                if (d.pool_oh <= 0)
+                    o = getPoolingOutputDimensionsFormula().compute(DimsHW(in0.d[1], in0.d[2]), d.ksize, d.stride, d.pad, DimsHW(1, 1), d.name.c_str());
+                if (o.h() <= 0 || o.w() <= 0) return fail(d, "empty output");
+                d.pool_oh = o.h(); d.pool_ow = o.w();
+                d.out[0]->dims = DimsCHW(in0.d[0], o.h(), o.w());
+                break;
+            }
+            case LKind::kFullyConnected:
+                if (d.nb_out_maps <= 0 || d.kw.count != static_cast<int64_t>(volume(in0)) * d.nb_out_maps) return fail(d, "fully connected: weight count mismatch");
+                if (d.bw.count != 0 && d.bw.count != d.nb_out_maps) return fail(d, "bias count mismatch");
+                d.out[0]->dims = DimsCHW(d.nb_out_maps, 1, 1);
+                break;
+            case LKind::kSoftMax:
+                if (in0.nbDims != 3) return fail(d, "soft-max expects a CHW input");
                 d.out[0]->dims = in0;
                 break;
             case LKind::kActivation:
@@ -483,6 +564,7 @@ public:
         for (auto* p : conv2d_plans_) rt_conv2d_destroy(p);
         for (auto* p : conv3d_plans_) rt_conv3d_destroy(p);
         for (auto* p : cvconv_plans_) rt_costvol_conv3d_destroy(p);
+        for (void* p : dev_blobs_) cudaFree(p);
     }
     int getNbBindings() const override { return static_cast<int>(bindings_.size()); }
     int getBindingIndex(const char* name) const override
@@ -532,6 +614,31 @@ public:
     std::vector<rt_conv3d_plan*> conv3d_plans_;
     std::vector<rt_cvconv_plan*> cvconv_plans_;
     std::vector<std::unique_ptr<ConvStep>> conv_steps_;
+    std::vector<void*> dev_blobs_;       // per-channel scale / shift arrays and fully-connected weights of the native layers
+
+    // Host weights (fp32 or fp16) -> device fp32 array of `count` elements (`fill` where the layer has none); nullptr on failure.
+    float* deviceArray(const Weights& w, int64_t count, float fill)
+    {
+        std::vector<float> h(static_cast<size_t>(count), fill);
+        if (w.values && w.count == count) {
+            if (w.type == DataType::kHALF) {
+                const uint16_t* s = static_cast<const uint16_t*>(w.values);
+                for (int64_t i = 0; i < count; ++i) {           // fp16 -> fp32 on the host
+                    const uint32_t sign = (s[i] >> 15) & 1u, ex = (s[i] >> 10) & 31u, man = s[i] & 1023u;
+                    float v;
+                    if (ex == 0) v = ldexpf(static_cast<float>(man), -24);
+                    else if (ex == 31) v = man ? NAN : INFINITY;
+                    else v = ldexpf(static_cast<float>(man | 1024u), static_cast<int>(ex) - 25);
+                    h[static_cast<size_t>(i)] = sign ? -v : v;
+                }
+            } else memcpy(h.data(), w.values, static_cast<size_t>(count) * sizeof(float));
+        }
+        void* d = nullptr;
+        if (cudaMalloc(&d, h.size() * sizeof(float)) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+        dev_blobs_.push_back(d);
+        return static_cast<float*>(d);
+    }
 
 private:
     bool fail(const std::string& s) { logMsg(log_, ILogger::Severity::kERROR, s); return false; }
@@ -549,7 +656,7 @@ ContextImpl::ContextImpl(EngineImpl* e) : engine_(e)
     if (alloc_ok_ && e->workspace_bytes_ > 0) alloc_ok_ = cudaMalloc(&workspace_, e->workspace_bytes_) == cudaSuccess;
     if (!alloc_ok_) logMsg(e->log_, ILogger::Severity::kERROR, "createExecutionContext: cudaMalloc of the activation arena / workspace failed");
     const char* g = getenv("REDTAIL_ENGINE_GRAPH");
-    graphs_enabled_ = !(g && g[0] == '0') && e->graph_safe_;
+    graphs_enabled_ = !(g && g[0] == '0') && e->graph_safe_ && getenv("REDTAIL_ENGINE_TRACE") == nullptr;   // tracing synchronises every step
 }
 
 // Eager the first time a (batch, bindings) pair is seen (first-use work such as cudaFuncSetAttribute happens there),
@@ -767,6 +874,46 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                 break;
             }
             case LKind::kScale: {
+                if (d.smode == ScaleMode::kCHANNEL) {
+                    // Caffe Scale layer with per-channel blobs (TrailNet_SResNet-18.prototxt: sub_mean and the S-ReLU chains).
+                    const int c = d.in[0]->dims.d[0];
+                    const int64_t hw = static_cast<int64_t>(d.in[0]->dims.d[1]) * d.in[0]->dims.d[2];
+                    if (d.power.count > 0) {
+                        std::vector<float> pw(static_cast<size_t>(c), 1.f);
+                        if (d.power.type == DataType::kFLOAT) memcpy(pw.data(), d.power.values, sizeof(float) * c);
+                        for (float v : pw) if (v != 1.f) return fail(d.name + ": per-channel scale with power != 1 is not supported");
+                    }
+                    const int in_id = d.in[0]->id;
+                    float* s1 = d.scale.count ? deviceArray(d.scale, c, 1.f) : nullptr;
+                    float* b1 = d.shift.count ? deviceArray(d.shift, c, 0.f) : nullptr;
+                    if ((d.scale.count && !s1) || (d.shift.count && !b1)) return fail(d.name + ": device allocation failed");
+                    // S-ReLU = Scale -> ReLU -> Scale (prototxt:54-105): one pass instead of three.
+                    const int n1 = fusion ? soleConsumer(d.out[0]) : -1;
+                    if (n1 >= 0 && net.layers_[n1]->d.kind == LKind::kActivation && net.layers_[n1]->d.act == ActivationType::kRELU) {
+                        const int n2 = soleConsumer(net.layers_[n1]->d.out[0]);
+                        if (n2 >= 0 && net.layers_[n2]->d.kind == LKind::kScale && net.layers_[n2]->d.smode == ScaleMode::kCHANNEL &&
+                            net.layers_[n2]->d.power.count == 0) {
+                            LayerData& d2 = net.layers_[n2]->d;
+                            float* s2 = d2.scale.count ? deviceArray(d2.scale, c, 1.f) : nullptr;
+                            float* b2 = d2.shift.count ? deviceArray(d2.shift, c, 0.f) : nullptr;
+                            if ((d2.scale.count && !s2) || (d2.shift.count && !b2)) return fail(d2.name + ": device allocation failed");
+                            done[n1] = done[n2] = true;
+                            st.name += " + " + net.layers_[n1]->d.name + " + " + d2.name;
+                            const int out_id = d2.out[0]->id;
+                            st.out.push_back(out_id);
+                            st.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                                return rt_srelu(ptr(in_id), ptr(out_id), batch, c, hw, s1, b1, s2, b2, s);
+                            };
+                            break;
+                        }
+                    }
+                    const int out_id = d.out[0]->id;
+                    st.out.push_back(out_id);
+                    st.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                        return rt_scale_channel(ptr(in_id), ptr(out_id), batch, c, hw, s1, b1, s);
+                    };
+                    break;
+                }
                 const float shift = weightScalar(d.shift, 0.f), scale = weightScalar(d.scale, 1.f), power = weightScalar(d.power, 1.f);
                 const int in_id = d.in[0]->id, out_id = d.out[0]->id;
                 // (x * 1 + 0)^1: the generator emits this identity in front of every tower (tensorrt_model_builder.py:134-136,
@@ -782,8 +929,50 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                 };
                 break;
             }
+            case LKind::kPooling: {
+                const int in_id = d.in[0]->id, out_id = d.out[0]->id;
+                const int c = d.in[0]->dims.d[0], h = d.in[0]->dims.d[1], w = d.in[0]->dims.d[2];
+                const int oh = d.pool_oh, ow = d.pool_ow, k = d.ksize.h(), stp = d.stride.h(), pd = d.pad.h();
+                const int is_max = d.pool == PoolingType::kMAX ? 1 : 0;
+                st.out.push_back(out_id);
+                st.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                    return rt_pool2d(ptr(in_id), ptr(out_id), batch, c, h, w, oh, ow, k, stp, pd, is_max, s);
+                };
+                break;
+            }
+            case LKind::kFullyConnected: {
+                const int in_id = d.in[0]->id, out_id = d.out[0]->id;
+                const int k = static_cast<int>(volume(d.in[0]->dims)), m = d.nb_out_maps;
+                float* wd = deviceArray(d.kw, static_cast<int64_t>(k) * m, 0.f);
+                float* bd = d.bw.count ? deviceArray(d.bw, m, 0.f) : nullptr;
+                if (!wd || (d.bw.count && !bd)) return fail(d.name + ": device allocation failed");
+                st.out.push_back(out_id);
+                st.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                    return rt_fully_connected(ptr(in_id), wd, bd, ptr(out_id), batch, k, m, s);
+                };
+                break;
+            }
+            case LKind::kSoftMax: {
+                const int in_id = d.in[0]->id, out_id = d.out[0]->id;
+                const int c = d.in[0]->dims.d[0];
+                const int64_t inner = static_cast<int64_t>(d.in[0]->dims.d[1]) * d.in[0]->dims.d[2];
+                st.out.push_back(out_id);
+                st.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                    return rt_softmax_channels(ptr(in_id), ptr(out_id), batch, c, inner, s);
+                };
+                break;
+            }
             case LKind::kActivation: {
-                if (d.act != ActivationType::kSIGMOID) return fail(d.name + ": only ActivationType::kSIGMOID is supported");
+                if (d.act == ActivationType::kRELU) {
+                    const int in_id = d.in[0]->id, out_id = d.out[0]->id;
+                    const int64_t elems = static_cast<int64_t>(slots_[in_id].elems);
+                    st.out.push_back(out_id);
+                    st.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                        return rt_relu(ptr(in_id), ptr(out_id), elems * batch, s);
+                    };
+                    break;
+                }
+                if (d.act != ActivationType::kSIGMOID) return fail(d.name + ": only ActivationType::kSIGMOID / kRELU are supported");
                 const int in_id = d.in[0]->id, out_id = d.out[0]->id;
                 const int64_t elems = static_cast<int64_t>(slots_[in_id].elems);
                 st.out.push_back(out_id);
@@ -1058,6 +1247,13 @@ std::string EngineImpl::serializeNetwork(NetworkImpl& net, int max_batch, bool h
             case LKind::kEltwise: w.put<int32_t>(static_cast<int32_t>(d.eop)); break;
             case LKind::kConcat: break;
             case LKind::kShuffle: w.put<uint8_t>(d.has_reshape ? 1 : 0); w.dims(d.reshape); break;
+            case LKind::kPooling:
+                w.put<int32_t>(static_cast<int32_t>(d.pool));
+                w.put<int32_t>(d.ksize.h()); w.put<int32_t>(d.stride.h()); w.put<int32_t>(d.pad.h());
+                w.put<int32_t>(d.pool_oh); w.put<int32_t>(d.pool_ow);
+                break;
+            case LKind::kFullyConnected: w.put<int32_t>(d.nb_out_maps); w.weights(d.kw); w.weights(d.bw); break;
+            case LKind::kSoftMax: break;
             case LKind::kPlugin: {
                 const size_t n = d.plugin->getSerializationSize();
                 if (n == 0) return std::string();          // a third-party plugin without serialisation: no plan
@@ -1368,6 +1564,18 @@ bool EngineImpl::planMemory()
         arena_bytes_ = std::max(arena_bytes_, off + sz);
         placed.push_back(id);
     }
+    if (getenv("REDTAIL_ENGINE_DUMP_PLAN")) {      // debugging aid: the memory plan on stderr
+        for (int id : order)
+            fprintf(stderr, "[redtail] tensor %3d %-40s off %12zu bytes %12zu live [%d, %d]%s\n", id, slots_[id].name.c_str(), slots_[id].offset,
+                    bytesOf(id), slots_[id].first, slots_[id].last, slots_[id].has_partner ? " (pair)" : "");
+        for (size_t si = 0; si < steps_.size(); ++si) {
+            fprintf(stderr, "[redtail] step %3zu %-60s ws %zu in", si, steps_[si].name.substr(0, 60).c_str(), steps_[si].workspace);
+            for (int id : steps_[si].in) fprintf(stderr, " %d", id);
+            fprintf(stderr, " out");
+            for (int id : steps_[si].out) fprintf(stderr, " %d", id);
+            fprintf(stderr, "\n");
+        }
+    }
     workspace_bytes_ = 0;
     for (auto& s : steps_) workspace_bytes_ = std::max(workspace_bytes_, s.workspace);
     logMsg(log_, ILogger::Severity::kINFO, "engine: " + std::to_string(steps_.size()) + " steps, activation arena " +
@@ -1404,8 +1612,15 @@ bool ContextImpl::run(int batchSize, void** bindings, cudaStream_t stream, bool 
         cudaEventRecord(ev[0], stream);
     }
     bool ok = true;
+    static const bool trace = getenv("REDTAIL_ENGINE_TRACE") != nullptr;      // debugging aid: name every step on stderr and wait for it
     for (size_t i = 0; i < e.steps_.size(); ++i) {
+        if (trace) { fprintf(stderr, "[redtail] step %zu %s ...", i, e.steps_[i].name.c_str()); fflush(stderr); }
         const int rc = e.steps_[i].run(batchSize, ptr, workspace_, stream);
+        if (trace) {
+            const cudaError_t ce = cudaStreamSynchronize(stream);
+            fprintf(stderr, " rc %d, %s\n", rc, cudaGetErrorString(ce));
+            fflush(stderr);
+        }
         if (rc != 0) {
             logMsg(e.log_, ILogger::Severity::kERROR, e.steps_[i].name + ": enqueue failed with status " + std::to_string(rc));
             ok = false;
@@ -1592,6 +1807,24 @@ public:
                                 : net->addPlugin(in.data(), static_cast<int>(in.size()), *plugin);
                     break;
                 }
+                case LKind::kPooling: {
+                    const PoolingType pt = static_cast<PoolingType>(r.get<int32_t>());
+                    const int k = r.get<int32_t>(), st2 = r.get<int32_t>(), pd = r.get<int32_t>();
+                    const int oh = r.get<int32_t>(), ow = r.get<int32_t>();
+                    auto* l = net->addPooling(*in[0], pt, DimsHW(k, k));
+                    l->setStride(DimsHW(st2, st2)); l->setPadding(DimsHW(pd, pd));
+                    net->pool_from_plan_ = true;
+                    static_cast<PoolingLayer*>(l)->d.pool_oh = oh; static_cast<PoolingLayer*>(l)->d.pool_ow = ow;
+                    layer = l;
+                    break;
+                }
+                case LKind::kFullyConnected: {
+                    const int maps = r.get<int32_t>();
+                    const Weights kw = r.weights(), bw = r.weights();
+                    layer = net->addFullyConnected(*in[0], maps, kw, bw);
+                    break;
+                }
+                case LKind::kSoftMax: layer = net->addSoftMax(*in[0]); break;
                 default: return fail("unknown layer kind in plan");
             }
             if (!r.ok || layer == nullptr) return fail(name + ": truncated plan");

@@ -16,7 +16,10 @@
 
 #include "internal_utils.h"
 #include "redtail_b200.h"
+#include "NvCaffeParser.h"
 #include "redtail_b200_engine.h"
+
+extern "C" size_t redtail_serialize_network(void* network, int max_batch, int half2, void* buf, size_t buf_len);
 
 using namespace nvinfer1;
 using namespace redtail::tensorrt;
@@ -432,5 +435,190 @@ int rt_stereo_profile(rt_stereo_engine* e, int batch, const float* left, const f
 
 int rt_stereo_num_layers(const rt_stereo_engine* e) { return e && e->engine ? e->engine->getNbLayers() : 0; }
 size_t rt_stereo_device_bytes(const rt_stereo_engine* e) { return e && e->engine ? e->engine->getWorkspaceSize() : 0; }
+
+// ---- Caffe classifier networks (include/redtail_b200_engine.h, rt_net_*) ----------------------------------------------------
+}  // extern "C"
+
+struct rt_net_engine {
+    CapiLogger log;
+    ICudaEngine* engine = nullptr;
+    IExecutionContext* context = nullptr;
+    int in_idx = 0, out_idx = 1;
+    size_t in_elems = 0, out_elems = 0;
+    int in_chw[3] = {0, 0, 0}, out_chw[3] = {0, 0, 0};
+    int max_batch = 1;
+    float* d_in = nullptr;
+    float* d_out = nullptr;
+    cudaStream_t stream = nullptr;
+};
+
+namespace {
+int finishNetEngine(std::unique_ptr<rt_net_engine>& e, rt_net_engine** out)
+{
+    if (e->engine->getNbBindings() != 2 || !e->engine->bindingIsInput(0) || e->engine->bindingIsInput(1)) {
+        g_last_error = "rt_net: the network must have exactly one input and one output";
+        rt_net_destroy(e.release());
+        return RT_ERR_UNSUPPORTED;
+    }
+    e->in_idx = 0; e->out_idx = 1;
+    const Dims id = e->engine->getBindingDimensions(0), od = e->engine->getBindingDimensions(1);
+    e->in_elems = 1; e->out_elems = 1;
+    for (int i = 0; i < 3; ++i) {
+        e->in_chw[i] = i < id.nbDims ? id.d[i] : 1; e->out_chw[i] = i < od.nbDims ? od.d[i] : 1;
+        e->in_elems *= static_cast<size_t>(e->in_chw[i]); e->out_elems *= static_cast<size_t>(e->out_chw[i]);
+    }
+    e->max_batch = e->engine->getMaxBatchSize();
+    e->context = e->engine->createExecutionContext();
+    if (!e->context || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_last_error = "rt_net: context / stream creation failed";
+        rt_net_destroy(e.release());
+        return RT_ERR_NO_DEVICE;
+    }
+    *out = e.release();
+    return RT_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int rt_caffe_create(const char* prototxt_path, const char* caffemodel_path, const char* input_blob, const char* output_blob,
+                    int max_batch, rt_net_engine** out)
+{
+    if (!prototxt_path || !caffemodel_path || !output_blob || !out || max_batch <= 0) { g_last_error = "rt_caffe_create: bad argument"; return RT_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_last_error = "rt_caffe_create: no CUDA device -- this engine has no CPU path";
+        return RT_ERR_NO_DEVICE;
+    }
+    std::unique_ptr<rt_net_engine> e(new rt_net_engine());
+    IBuilder* builder = createInferBuilder(e->log);
+    INetworkDefinition* net = builder->createNetwork();
+    nvcaffeparser1::ICaffeParser* parser = nvcaffeparser1::createCaffeParser();
+    const nvcaffeparser1::IBlobNameToTensor* blobs = parser->parse(prototxt_path, caffemodel_path, *net, DataType::kFLOAT);
+    ITensor* ob = blobs ? blobs->find(output_blob) : nullptr;
+    if (!blobs || !ob || (input_blob && blobs->find(input_blob) == nullptr)) {
+        g_last_error = !blobs ? std::string("rt_caffe_create: could not parse ") + prototxt_path + " / " + caffemodel_path
+                              : std::string("rt_caffe_create: blob not found: ") + (ob ? input_blob : output_blob);
+        net->destroy(); parser->destroy(); builder->destroy();
+        return RT_ERR_ARG;
+    }
+    net->markOutput(*ob);
+    builder->setMaxBatchSize(max_batch);
+    builder->setMaxWorkspaceSize(static_cast<size_t>(1) << 30);
+    e->engine = builder->buildCudaEngine(*net);
+    net->destroy(); parser->destroy(); builder->destroy();
+    if (!e->engine) { g_last_error = "rt_caffe_create: engine build failed: " + e->log.last_error; return RT_ERR_UNSUPPORTED; }
+    return finishNetEngine(e, out);
+}
+
+void rt_net_destroy(rt_net_engine* e)
+{
+    if (!e) return;
+    if (e->context) e->context->destroy();
+    if (e->engine) e->engine->destroy();
+    cudaFree(e->d_in); cudaFree(e->d_out);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int rt_net_dims(const rt_net_engine* e, int in_chw[3], int out_chw[3])
+{
+    if (!e || !in_chw || !out_chw) return RT_ERR_ARG;
+    for (int i = 0; i < 3; ++i) { in_chw[i] = e->in_chw[i]; out_chw[i] = e->out_chw[i]; }
+    return RT_OK;
+}
+
+int rt_net_enqueue(rt_net_engine* e, int batch, const float* in, float* out, void* stream)
+{
+    if (!e || !in || !out || batch < 1 || batch > e->max_batch) return RT_ERR_ARG;
+    void* bindings[2];
+    bindings[e->in_idx] = const_cast<float*>(in);
+    bindings[e->out_idx] = out;
+    return e->context->enqueue(batch, bindings, static_cast<cudaStream_t>(stream), nullptr) ? RT_OK : RT_ERR_UNSUPPORTED;
+}
+
+int rt_net_execute_host(rt_net_engine* e, int batch, const float* in, float* out)
+{
+    if (!e || !in || !out || batch < 1 || batch > e->max_batch) return RT_ERR_ARG;
+    if (!e->d_in) {
+        if (cudaMalloc(reinterpret_cast<void**>(&e->d_in), e->in_elems * sizeof(float) * e->max_batch) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&e->d_out), e->out_elems * sizeof(float) * e->max_batch) != cudaSuccess) return RT_ERR_NO_DEVICE;
+    }
+    cudaError_t err = cudaMemcpyAsync(e->d_in, in, e->in_elems * sizeof(float) * batch, cudaMemcpyHostToDevice, e->stream);
+    if (err != cudaSuccess) return static_cast<int>(err);
+    const int rc = rt_net_enqueue(e, batch, e->d_in, e->d_out, e->stream);
+    if (rc != RT_OK) return rc;
+    err = cudaMemcpyAsync(out, e->d_out, e->out_elems * sizeof(float) * batch, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    return static_cast<int>(err);
+}
+
+int rt_net_profile(rt_net_engine* e, int batch, const float* in, float* out, char* buf, size_t buf_len)
+{
+    if (!e || !in || !out || !buf || buf_len == 0 || batch < 1 || batch > e->max_batch) return RT_ERR_ARG;
+    LayerTimer timer;
+    e->context->setProfiler(&timer);
+    void* bindings[2];
+    bindings[e->in_idx] = const_cast<float*>(in);
+    bindings[e->out_idx] = out;
+    const bool ok = e->context->execute(batch, bindings);
+    e->context->setProfiler(nullptr);
+    if (!ok) return RT_ERR_UNSUPPORTED;
+    std::ostringstream s;
+    for (auto& r : timer.rows) s << r.first << "\t" << r.second << "\n";
+    const std::string str = s.str();
+    strncpy(buf, str.c_str(), buf_len - 1);
+    buf[buf_len - 1] = 0;
+    return RT_OK;
+}
+
+size_t rt_net_serialize(const rt_net_engine* e, void* buf, size_t buf_len)
+{
+    if (!e || !e->engine) return 0;
+    IHostMemory* m = e->engine->serialize();
+    if (!m) return 0;
+    const size_t n = m->size();
+    if (buf && buf_len >= n) memcpy(buf, m->data(), n);
+    m->destroy();
+    return n;
+}
+
+int rt_net_deserialize(const void* plan, size_t plan_size, int max_batch, rt_net_engine** out)
+{
+    // plan header: 8-byte magic, int32 version, int32 max batch (engine.cpp, serializeNetwork)
+    if (!plan || plan_size < 16 || !out) { g_last_error = "rt_net_deserialize: bad argument"; return RT_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_last_error = "rt_net_deserialize: no CUDA device"; return RT_ERR_NO_DEVICE; }
+    std::string copy(static_cast<const char*>(plan), plan_size);
+    if (max_batch > 0) { const int32_t mb = max_batch; memcpy(&copy[12], &mb, 4); }
+    std::unique_ptr<rt_net_engine> e(new rt_net_engine());
+    IRuntime* rt = createInferRuntime(e->log);
+    e->engine = rt->deserializeCudaEngine(copy.data(), copy.size(), nullptr);
+    rt->destroy();
+    if (!e->engine) { g_last_error = "rt_net_deserialize: " + e->log.last_error; return RT_ERR_ARG; }
+    return finishNetEngine(e, out);
+}
+
+int rt_net_num_layers(const rt_net_engine* e) { return e && e->engine ? e->engine->getNbLayers() : 0; }
+
+// Host-only (no CUDA device needed): parse the Caffe model and write the network's plan without building an engine -- what
+// rt_net_serialize would return.  Lets the CPU test-suite check the parser with its float64 graph-level checker.
+size_t rt_caffe_dump_plan(const char* prototxt_path, const char* caffemodel_path, const char* output_blob, int max_batch, void* buf, size_t buf_len)
+{
+    if (!prototxt_path || !caffemodel_path || !output_blob) return 0;
+    CapiLogger log;
+    IBuilder* builder = createInferBuilder(log);
+    INetworkDefinition* net = builder->createNetwork();
+    nvcaffeparser1::ICaffeParser* parser = nvcaffeparser1::createCaffeParser();
+    const nvcaffeparser1::IBlobNameToTensor* blobs = parser->parse(prototxt_path, caffemodel_path, *net, DataType::kFLOAT);
+    ITensor* ob = blobs ? blobs->find(output_blob) : nullptr;
+    size_t n = 0;
+    if (ob) {
+        net->markOutput(*ob);
+        n = redtail_serialize_network(net, max_batch, 0, buf, buf_len);
+    } else g_last_error = "rt_caffe_dump_plan: parse failed or output blob not found";
+    net->destroy(); parser->destroy(); builder->destroy();
+    return n;
+}
 
 }  // extern "C"

@@ -71,15 +71,16 @@ __device__ __forceinline__ void zero16(float (&a)[16]) {
 }
 
 // Output phase of one finished plane: D0 + D1 / 2048 + bias -> ELU -> split16 stores of this thread's 8 channels.
-__device__ __forceinline__ void emit_plane(const DsParams& p, const float (&a)[16], const float* s_bias, __half* out, int n, int q,
-                                           int h, int w, int g) {
-    if (h >= p.out_h || w >= p.out_w || g * 8 >= p.cout) return;
-    const long long idx = n * p.out_sn + ((static_cast<long long>(q) * p.out_h + h) * p.out_w + w) * p.cout + g * 8;
+// `base` = element offset of (sample, plane 0, this thread's position, channel group), < 0 when the thread has no output.
+__device__ __forceinline__ void emit_plane(const DsParams& p, const float (&a)[16], const float* s_bias8, __half* out, long long base, int q) {
+    if (base < 0) return;
+    const long long idx = base + static_cast<long long>(q) * p.out_h * p.out_w * p.cout;
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        v[j] = fmaf(a[8 + j], 1.f / 2048.f, a[j]) + s_bias[g * 8 + j];
-        if (p.fuse_elu) v[j] = elu1(v[j]);
+    for (int j = 0; j < 8; j += 2) {                        // packed fp32 pairs: same operations as the scalar form
+        const f32x2 r = add2(fma2(pk2(a[8 + j], a[9 + j]), bc2(1.f / 2048.f), pk2(a[j], a[j + 1])), pk2(s_bias8[j], s_bias8[j + 1]));
+        upk2(r, v[j], v[j + 1]);
+        if (p.fuse_elu) elu1_x2(v[j], v[j + 1]);
     }
     uint4 hv, lv;
     split8_packed(v, hv, lv);
@@ -198,8 +199,13 @@ conv3d_ds_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         int buf = 0;
         uint32_t bphase = 0;
         for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
-            const int n = job / p.tiles_per_sample, r = job - n * p.tiles_per_sample;
-            const int w = (r % p.tiles_w) * kTw + wl, h = (r / p.tiles_w) * kTh + hl;
+            long long base;
+            {
+                const int n = job / p.tiles_per_sample, r = job - n * p.tiles_per_sample;
+                const int w = (r % p.tiles_w) * kTw + wl, h = (r / p.tiles_w) * kTh + hl;
+                base = (h < p.out_h && w < p.out_w && g * 8 < p.cout)
+                           ? n * p.out_sn + (static_cast<long long>(h) * p.out_w + w) * p.cout + g * 8 : -1;
+            }
             float acc[3][16];                            // [output plane mod 3][D0 x 8 | D1 x 8]
             zero16(acc[0]); zero16(acc[1]); zero16(acc[2]);
             for (int pl0 = 0; pl0 < p.depth; pl0 += 3) {
@@ -213,16 +219,13 @@ conv3d_ds_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                             const uint32_t t0 = lane_base + static_cast<uint32_t>(buf * kBufCols);
 #pragma unroll
                             for (int v = 0; v < 3; ++v) {                          // filter plane v -> output plane pl + 1 - v
+                                float (&a)[16] = acc[(rr + 4 - v) % 3];
                                 uint32_t x0[8], x1[8];
                                 tmem_ld8(t0 + v * kCoutPad, x0);
                                 tmem_ld8(t0 + 3 * kCoutPad + v * kCoutPad, x1);
                                 tmem_ld_wait();
-                                float (&a)[16] = acc[(rr + 4 - v) % 3];
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) {
-                                    a[k] += __uint_as_float(x0[k]);
-                                    a[8 + k] += __uint_as_float(x1[k]);
-                                }
+                                add_pairs<8>(&a[0], reinterpret_cast<const float*>(x0));
+                                add_pairs<8>(&a[8], reinterpret_cast<const float*>(x1));
                             }
                             tc_fence_before();
                             __syncwarp();
@@ -230,7 +233,7 @@ conv3d_ds_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                             if (++buf == kNumBuf) { buf = 0; bphase ^= 1; }
                         }
                         // input plane pl is done: output plane pl - 1 (set (rr + 2) % 3) is complete
-                        if (pl >= 1) emit_plane(p, acc[(rr + 2) % 3], s_bias, out, n, pl - 1, h, w, g);
+                        if (pl >= 1) emit_plane(p, acc[(rr + 2) % 3], s_bias + g * 8, out, base, pl - 1);
                         zero16(acc[(rr + 2) % 3]);
                     }
                 }
@@ -238,9 +241,9 @@ conv3d_ds_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             // the last output plane (it has no input plane after it)
             const int last = p.depth - 1;
             switch (last % 3) {
-                case 0: emit_plane(p, acc[0], s_bias, out, n, last, h, w, g); break;
-                case 1: emit_plane(p, acc[1], s_bias, out, n, last, h, w, g); break;
-                default: emit_plane(p, acc[2], s_bias, out, n, last, h, w, g); break;
+                case 0: emit_plane(p, acc[0], s_bias + g * 8, out, base, last); break;
+                case 1: emit_plane(p, acc[1], s_bias + g * 8, out, base, last); break;
+                default: emit_plane(p, acc[2], s_bias + g * 8, out, base, last); break;
             }
         }
     }

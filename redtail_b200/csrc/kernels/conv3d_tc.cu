@@ -108,7 +108,8 @@ struct TcParams {
     int fuse_elu;
     int out_split;           // 1: y (and skip) are RT_LAYOUT_SPLIT16, 0: dense fp32
     int dbg;                 // timing experiments only (REDTAIL_TC_DEBUG bit mask; results are garbage): 1 = epilogue skips the
-                             // tcgen05.ld drains, 2 = no MMAs are issued, 4 = the producer moves no data, 8 = no output phase (bias/ELU/stores)
+                             // tcgen05.ld drains, 2 = no MMAs are issued, 4 = the producer moves no data, 8 = no output phase (bias/ELU/stores);
+                             // A/B switches with correct results: 16 = L2 prefetch of the skip tensor at tile start, 32 = skip vectors loaded per batch
     int out_c;               // channels of the output tensor (split16 addressing)
     long long out_lo;        // split16: offset of the lo plane, in halves
     int interleave;          // > 0 (experiment, REDTAIL_TC_INTERLEAVE=1): job index = tile * nclasses + class over the common tile
@@ -254,7 +255,11 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         prefetch_tensormap(&map_a_hi);
         if (SPLIT) prefetch_tensormap(&map_a_lo);
         prefetch_tensormap(&map_w);
-        for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        // A slot is free again when BOTH issuing warps are done with it: the one that issued its MMAs (tcgen05.commit) and the one
+        // that only observed its full barrier (plain arrive) -- see the observer branch of the issuing loop.  With sub-stage chunks
+        // only warp 1 issues (and observes), so one arrival frees the slot.
+        const uint32_t slot_arrivals = p.chunk_rows >= p.gr ? kMmaWarps : 1;
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], slot_arrivals); }
         for (int i = 0; i < kNumBuf; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EW); }
         fence_barrier_init();
     }
@@ -364,6 +369,13 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                             // phase p+1 of a slot before phase p had completed would see "complete" at once (parity aliasing).
                             // Watching every phase of every slot in order keeps both warps within one phase of each barrier.
                             mbar_wait(&full_bar[stage], phase);
+                            // ... and tell the producer so.  Observing alone is not enough: a slot whose consecutive fills all belong
+                            // to the OTHER warp (even ring sizes with one-stage chunks, or two-stage chunks on a 3-slot ring) could be
+                            // consumed and refilled twice while this warp is held up elsewhere (its own MMAs queue behind the other
+                            // warp's); it would then wait for the fill after next, run two fills late for the rest of the kernel
+                            // and hang on the last one, which never comes (seen as an intermittent hang of the ResNet-18 decoder
+                            // layers at batch 4..8).  The slot's empty barrier therefore needs this warp's arrival too.
+                            if (lane == 0) mbar_arrive(&empty_bar[stage]);
                             if (close) {
                                 kb_in_chunk = 0; ++chunk_idx;
                                 if (++buf == kNumBuf) { buf = 0; bphase ^= 1; }
@@ -483,9 +495,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             if (jc.empty) continue;
             const ClassInfo& ci = p.cls[jc.cls];
             const int nkb = ci.ntaps * p.ncb;
-            // The skip tensor is read once, long after this point: ask L2 for this tile's lines now so that the output phase
-            // does not wait for HBM (split16 outputs only; the transposed convs of the decoder are the layers with a skip).
-            if (skip != nullptr && p.out_split) {
+            // Experiment (REDTAIL_TC_DEBUG=16): ask L2 for this tile's skip lines at the start of the tile.  Measured on NVSmall:
+            // deconv3D_2 0.514 -> 0.568 ms, deconv3D_1 0.182 -> 0.196 ms WITH the prefetch -- the extra requests cost more than
+            // the (already overlapped) latency they hide; off by default.
+            if (skip != nullptr && p.out_split && (p.dbg & 16)) {
                 const __half* sk16 = reinterpret_cast<const __half*>(skip);
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
@@ -544,11 +557,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                             }
                             tmem_ld_wait();
                         }
-#pragma unroll
-                        for (int k = 0; k < BW; ++k) {
-                            acc0[mt][b0 + k] += __uint_as_float(v0[k]);
-                            if (SPLIT) acc1[mt][b0 + k] += __uint_as_float(v1[k]);
-                        }
+                        add_pairs<BW>(&acc0[mt][b0], reinterpret_cast<const float*>(v0));
+                        if (SPLIT) add_pairs<BW>(&acc1[mt][b0], reinterpret_cast<const float*>(v1));
                     }
                 }
                 tc_fence_before();
@@ -561,7 +571,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int k = 0; k < CPH; ++k) acc0[mt][k] = fmaf(acc1[mt][k], 1.f / 2048.f, acc0[mt][k]);
+                    for (int k = 0; k < CPH; k += 2)
+                        upk2(fma2(pk2(acc1[mt][k], acc1[mt][k + 1]), bc2(1.f / 2048.f), pk2(acc0[mt][k], acc0[mt][k + 1])), acc0[mt][k], acc0[mt][k + 1]);
             }
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
@@ -587,7 +598,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     // exposed memory latency per tile instead of one per batch of 8 columns
                     constexpr bool kUpFront = CPH <= 32;          // 64 columns per thread: the vectors would not fit in registers
                     uint4 sh[kUpFront ? CPH / 8 : 1], sl[kUpFront ? CPH / 8 : 1];
-                    if (skip && kUpFront) {
+                    const bool up_front = kUpFront && !(p.dbg & 32);
+                    if (skip && up_front) {
 #pragma unroll
                         for (int k0 = 0; k0 < CPH; k0 += 8) {
                             const ColInfo c0 = s_col[col0 + k0];
@@ -608,9 +620,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                                 v[j] = acc0[mt][k0 + j] + s_bias[c0.ch + j];
                             }
                             if (skip) {
-                                if (!kUpFront) {
-                                    sh[0] = __ldg(reinterpret_cast<const uint4*>(sk16 + idx));
-                                    sl[0] = __ldg(reinterpret_cast<const uint4*>(sk16 + p.out_lo + idx));
+                                if (!up_front) {
+                                    sh[kUpFront ? k0 / 8 : 0] = __ldg(reinterpret_cast<const uint4*>(sk16 + idx));
+                                    sl[kUpFront ? k0 / 8 : 0] = __ldg(reinterpret_cast<const uint4*>(sk16 + p.out_lo + idx));
                                 }
                                 const __half* hh = reinterpret_cast<const __half*>(&sh[kUpFront ? k0 / 8 : 0]);
                                 const __half* ll = reinterpret_cast<const __half*>(&sl[kUpFront ? k0 / 8 : 0]);
@@ -619,7 +631,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                             }
                             if (p.fuse_elu) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] = elu1(v[j]);
+                                for (int j = 0; j < 8; j += 2) elu1_x2(v[j], v[j + 1]);
                             }
                             uint4 hv, lv;
                             split8_packed(v, hv, lv);

@@ -70,22 +70,6 @@ cvconv_edge_kernel(const float* __restrict__ right, const float* __restrict__ w_
     }
 }
 
-// fp32 x8 -> split16 (hi, lo) 16-byte vectors; `lo_clamp` false when the values are known to be >= -65504.
-__device__ __forceinline__ void split_store8_fast(const float (&v)[8], __half* hi, __half* lo) {
-    __align__(16) __half2 hv[4];
-    __align__(16) __half2 lv[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float x0 = fminf(fmaxf(v[2 * q], -65504.f), 65504.f), x1 = fminf(fmaxf(v[2 * q + 1], -65504.f), 65504.f);
-        const __half2 h2 = __floats2half2_rn(x0, x1);
-        const float2 hf = __half22float2(h2);
-        hv[q] = h2;
-        lv[q] = __floats2half2_rn((x0 - hf.x) * 2048.f, (x1 - hf.y) * 2048.f);
-    }
-    *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(hv);
-    *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(lv);
-}
-
 // One CTA: kXT consecutive x of one (n, y) row, all K channels, all D planes.  Thread = (x, 8-channel group), channel
 // group fastest so that the 16-byte stores of a warp are contiguous in the channels-last output.
 //   smem: S[pw][K] position-major, S[u] = C_0[u+1] + C_1[u] + C_2[u-1] for u in [x0-D, x0+kXT] (the interior planes'
@@ -144,12 +128,12 @@ cvconv_combine_kernel(const float* __restrict__ a, const float* __restrict__ cc,
         }
         if (fuse_elu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) val[j] = elu1_approx(val[j]);
+            for (int j = 0; j < 8; j += 2) elu1_x2(val[j], val[j + 1]);     // the library's one ELU (common.cuh), two lanes per instruction
         }
         if (kSplitOut) {
             __half* hi = static_cast<__half*>(out) + static_cast<long long>(n) * 2 * plane;
             const long long o = ((static_cast<long long>(d) * h + y) * w + x) * k + c0;
-            split_store8_fast(val, hi + o, hi + plane + o);
+            split_store8(val, hi + o, hi + plane + o);
         } else {
             float* o = static_cast<float*>(out);
 #pragma unroll
@@ -180,8 +164,11 @@ cvconv_combine_kernel(const float* __restrict__ a, const float* __restrict__ cc,
         const int i = xl + disp - d;                                        // staged index of u = x - d
         const float4 s0 = sm4[i * k4 + ((2 * kg) ^ (i & 1))];
         const float4 s1 = sm4[i * k4 + ((2 * kg + 1) ^ (i & 1))];
-        float val[8] = {base[0] + s0.x, base[1] + s0.y, base[2] + s0.z, base[3] + s0.w,
-                        base[4] + s1.x, base[5] + s1.y, base[6] + s1.z, base[7] + s1.w};
+        float val[8];
+        upk2(add2(pk2(base[0], base[1]), pk2(s0.x, s0.y)), val[0], val[1]);
+        upk2(add2(pk2(base[2], base[3]), pk2(s0.z, s0.w)), val[2], val[3]);
+        upk2(add2(pk2(base[4], base[5]), pk2(s1.x, s1.y)), val[4], val[5]);
+        upk2(add2(pk2(base[6], base[7]), pk2(s1.z, s1.w)), val[6], val[7]);
         emit(d, val);
     }
     {

@@ -118,3 +118,85 @@ class StereoEngine:
             self.close()
         except Exception:
             pass
+
+
+class CaffeNet:
+    """A single-input Caffe model (the TrailNet S-ResNet-18 classifier) through the nvcaffeparser1-compatible parser and the
+    engine: what ros/packages/caffe_ros/src/tensor_net.cpp does (loadNetwork / forward), minus the OpenCV pre-processing.
+
+    x: [N,C,H,W] fp32 (for TrailNet: BGR, 0..255, 180x320)  ->  [N,Co,Ho,Wo] fp32 (TrailNet: [N,6,1,1] softmax outputs).
+    """
+
+    def __init__(self, prototxt, caffemodel, output_blob, input_blob="data", max_batch=1, _handle=None):
+        if not torch.cuda.is_available():
+            raise RedtailError("CaffeNet needs a CUDA device (there is no CPU path)")
+        self.lib = engine_lib()
+        self._e = C.c_void_p()
+        if _handle is not None:
+            self._e = _handle
+        else:
+            rc = self.lib.rt_caffe_create(str(prototxt).encode(), str(caffemodel).encode(), input_blob.encode(), output_blob.encode(),
+                                          int(max_batch), C.byref(self._e))
+            if rc != 0:
+                raise RedtailError("rt_caffe_create failed (%d): %s" % (rc, self.lib.rt_stereo_last_error().decode()))
+        i3, o3 = (C.c_int * 3)(), (C.c_int * 3)()
+        self.lib.rt_net_dims(self._e, i3, o3)
+        self.in_chw, self.out_chw = tuple(i3), tuple(o3)
+
+    @classmethod
+    def deserialize(cls, plan, max_batch=0):
+        lib = engine_lib()
+        h = C.c_void_p()
+        rc = lib.rt_net_deserialize(plan, len(plan), int(max_batch), C.byref(h))
+        if rc != 0:
+            raise RedtailError("rt_net_deserialize failed (%d): %s" % (rc, lib.rt_stereo_last_error().decode()))
+        return cls(None, None, None, _handle=h)
+
+    def serialize(self):
+        n = self.lib.rt_net_serialize(self._e, None, 0)
+        if n == 0:
+            raise RedtailError("rt_net_serialize failed")
+        buf = C.create_string_buffer(n)
+        self.lib.rt_net_serialize(self._e, buf, n)
+        return buf.raw
+
+    def __call__(self, x, out=None):
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape[1:]) == self.in_chw, (x.shape, self.in_chw)
+        n = x.shape[0]
+        if out is None:
+            out = torch.empty((n,) + self.out_chw, dtype=torch.float32, device=x.device)
+        rc = self.lib.rt_net_enqueue(self._e, n, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()),
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise RedtailError("rt_net_enqueue failed (%d): %s" % (rc, self.lib.rt_stereo_last_error().decode()))
+        return out
+
+    def execute_host(self, x, out):
+        rc = self.lib.rt_net_execute_host(self._e, x.shape[0], C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()))
+        if rc != 0:
+            raise RedtailError("rt_net_execute_host failed (%d): %s" % (rc, self.lib.rt_stereo_last_error().decode()))
+        return out
+
+    def profile(self, x):
+        out = torch.empty((x.shape[0],) + self.out_chw, dtype=torch.float32, device=x.device)
+        buf = C.create_string_buffer(1 << 16)
+        torch.cuda.synchronize()
+        rc = self.lib.rt_net_profile(self._e, x.shape[0], C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), buf, len(buf))
+        if rc != 0:
+            raise RedtailError("rt_net_profile failed (%d)" % rc)
+        return [(l.rsplit("\t", 1)[0], float(l.rsplit("\t", 1)[1])) for l in buf.value.decode().splitlines()]
+
+    @property
+    def num_layers(self):
+        return self.lib.rt_net_num_layers(self._e)
+
+    def close(self):
+        if getattr(self, "_e", None):
+            self.lib.rt_net_destroy(self._e)
+            self._e = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

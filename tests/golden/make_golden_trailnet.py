@@ -1,0 +1,37 @@
+"""Generates the TrailNet fixtures (run where /root/reference and cv2 exist; the GPU box only reads the committed files):
+  tests/golden/trailnet/TrailNet_SResNet-18.{prototxt,caffemodel}   the reference's model files, byte for byte
+  tests/golden/trailnet/inputs.npz      the five test images of ros/packages/caffe_ros/tests/data as the network sees them:
+                                        cv::imread -> float -> cv::resize(320x180, INTER_CUBIC) -> CHW, BGR, 0..255
+                                        (ros/packages/caffe_ros/src/tensor_net.cpp:303-336 with the test node's defaults)
+  tests/golden/trailnet/expected.npz    `tests_cpp`: the predictions ros/packages/caffe_ros/tests/tests.cpp:64-69 expects (1e-3);
+                                        `oracle_f64`: oracle/caffe.py in float64 on the same inputs
+"""
+import os
+import shutil
+import sys
+
+import cv2
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle import caffe
+
+REF = "/root/reference"
+OUT = os.path.join(HERE, "trailnet")
+os.makedirs(OUT, exist_ok=True)
+for f in ("TrailNet_SResNet-18.prototxt", "TrailNet_SResNet-18.caffemodel"):
+    shutil.copyfile(os.path.join(REF, "models", "pretrained", f), os.path.join(OUT, f))
+names = ["rot_l.jpg", "rot_c.jpg", "rot_r.jpg", "tran_l.jpg", "tran_r.jpg"]
+tests_cpp = np.array([[0.932, 0.060, 0.006, 0.080, 0.848, 0.071],
+                      [0.040, 0.958, 0.001, 0.488, 0.375, 0.135],
+                      [0.000, 0.027, 0.971, 0.036, 0.407, 0.555],
+                      [0.011, 0.988, 0.000, 0.981, 0.008, 0.009],
+                      [0.000, 0.855, 0.144, 0.013, 0.031, 0.954]], np.float64)
+x = np.stack([caffe.preprocess_bgr8(cv2.imread(os.path.join(REF, "ros/packages/caffe_ros/tests/data", n)), 320, 180) for n in names])
+np.savez_compressed(os.path.join(OUT, "inputs.npz"), images=x.astype(np.float32), names=np.array(names))
+blobs = caffe.read_caffemodel(os.path.join(OUT, "TrailNet_SResNet-18.caffemodel"))
+proto = open(os.path.join(OUT, "TrailNet_SResNet-18.prototxt")).read()
+y = caffe.run_net(proto, blobs, x.astype(np.float64))
+print("max |oracle - tests.cpp| =", np.abs(y - tests_cpp).max())
+np.savez(os.path.join(OUT, "expected.npz"), tests_cpp=tests_cpp, oracle_f64=y)
