@@ -320,7 +320,7 @@ def run_other_config(args):
     for name, t_ms in eng.profile(d_left, d_right):
         acc[name] = acc.get(name, 0.0) + t_ms
     stack_ms = sum(t for n, t in acc.items() if n.startswith(cfg["stack_prefix"]))
-    tf = cfg["gflop_per_pair"] * B / stack_ms / 1e3 if stack_ms > 0 else 0.0
+    tf = cfg["gflop_per_pair"] * B / stack_ms if stack_ms > 0 else 0.0          # GFLOP / ms = TFLOP/s
     pairs = world * B * args.steps
     value = pairs / (ms * 1e-3)
     print(json.dumps({
@@ -341,13 +341,114 @@ def run_other_config(args):
         dist.destroy_process_group()
 
 
+def run_trailnet(args):
+    """bench.py --config trailnet: BASELINE configs[4], "TrailNet ResNet-18 320x180 batch=256 on 1 B200 (2D-conv tensor-core path,
+    orientation+translation heads)".  A step = one batch of synthetic 320x180 BGR frames through the S-ResNet-18 classifier
+    (models/pretrained/TrailNet_SResNet-18.{prototxt,caffemodel}, committed under tests/golden/trailnet/) loaded by the
+    nvcaffeparser1-compatible parser; unit = images/s.  Parity: the reference's five test images against the predictions its own
+    test expects (ros/packages/caffe_ros/tests/tests.cpp:64-69, 1e-3)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH,ENV")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from redtail_b200 import CaffeNet, ops
+    tn = os.path.join(ROOT, "tests", "golden", "trailnet")
+    B = args.batch if args.batch_given else 256
+    net = CaffeNet(os.path.join(tn, "TrailNet_SResNet-18.prototxt"), os.path.join(tn, "TrailNet_SResNet-18.caffemodel"), "out", max_batch=B)
+    rng = np.random.default_rng(1234 + rank)
+    h_in = torch.from_numpy(rng.uniform(0, 255, (B, 3, 180, 320)).astype(np.float32)).pin_memory()
+    h_out = torch.empty((B, 6, 1, 1), dtype=torch.float32).pin_memory()
+    d_in = h_in.cuda()
+    d_out = torch.empty((B, 6, 1, 1), dtype=torch.float32, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        net(d_in, out=d_out)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        net(d_in, out=d_out)
+    e1.record()
+    barrier()
+    launches = ops.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    for _ in range(2):
+        net.execute_host(h_in, h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        net.execute_host(h_in, h_out)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join()
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    x5 = np.load(os.path.join(tn, "inputs.npz"))["images"]
+    exp = np.load(os.path.join(tn, "expected.npz"))
+    reps = (B + 4) // 5
+    xb = torch.from_numpy(np.tile(x5, (reps, 1, 1, 1))[:B]).cuda()
+    y = net(xb).cpu().numpy().reshape(B, 6)
+    n5 = min(B, 5)
+    err_ref = float(np.abs(y[:n5] - exp["tests_cpp"][:n5]).max())
+    err_orc = float(np.abs(y[:n5] - exp["oracle_f64"][:n5]).max())
+    parity = {"max_abs_vs_reference_test": err_ref, "max_abs_vs_f64_oracle": err_orc, "tolerance": 1e-3, "pass": bool(err_ref <= 1e-3),
+              "vs": "predictions expected by ros/packages/caffe_ros/tests/tests.cpp:64-69 for the reference's five test images"}
+    peaks = measured_peaks()
+    acc = {}
+    for name, t_ms in net.profile(d_in):
+        acc[name] = acc.get(name, 0.0) + t_ms
+    conv_ms = sum(t for n, t in acc.items() if n.startswith(("conv", "res")) and "srelu" not in n.split(" + ")[0] and "sum" not in n.split(" + ")[0])
+    gflop_img = 5.20                                         # SURVEY.md 8(d): TrailNet 5.20 GFLOP / image
+    tf = gflop_img * B / conv_ms if conv_ms > 0 else 0.0     # GFLOP / ms = TFLOP/s
+    imgs = world * B * args.steps
+    print(json.dumps({
+        "metric": "images/sec TrailNet S-ResNet-18 320x180", "value": imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (fp16-split tensor-core products)", "data": "synthetic",
+        "config": {"workload": "TrailNet S-ResNet-18 320x180, batch=%d per GPU (BASELINE configs[4])" % B, "images_per_step": world * B,
+                   "parallelism": "dp%d (independent images)" % world, "l2": "activations of a 256-image batch (GBs) >> 126 MB L2; no explicit flush"},
+        "e2e": {"value": imgs / e2e_s, "unit": "images/s", "h2d_bytes_per_step": int(B * 3 * 180 * 320 * 4), "d2h_bytes_per_step": int(B * 6 * 4)},
+        "gpu_launches": int(launches), "parity": parity, "clocks": sampler.summary(),
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["tflops_sustained"],
+                     "traffic": None, "kernel": "the 20 convolutions of the net (steps named conv* / res*), algorithmic %.2f GFLOP/image" % gflop_img,
+                     "peak_source": peaks["source"] + " cuBLAS bf16 (sustained)", "share_of_step": conv_ms / sum(acc.values()) if acc else None},
+        "layer_ms": {k: round(v, 4) for k, v in acc.items()},
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=None, help="stereo pairs per GPU per step (default: the BASELINE config's: 1 for nvsmall)")
-    ap.add_argument("--config", default="nvsmall", choices=["nvsmall"] + sorted(OTHER_CONFIGS),
+    ap.add_argument("--config", default="nvsmall", choices=["nvsmall", "trailnet"] + sorted(OTHER_CONFIGS),
                     help="nvsmall = BASELINE configs[1] (the headline metric); the others are the remaining GPU configs of BASELINE.json")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -356,6 +457,9 @@ def main():
     if args.batch is None:
         args.batch = 1
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "ours" and args.config == "trailnet":
+        run_trailnet(args)
+        return
     if args.impl == "ours" and args.config != "nvsmall":
         run_other_config(args)
         return

@@ -36,8 +36,15 @@ namespace rt {
 namespace {
 
 constexpr int kEpiWarps = 16;
-constexpr int kThreads = 32 * (2 + kEpiWarps);      // warp 0: TMA producer, warp 1: MMA issuer, warps 2..17: epilogue
-constexpr int kStages = 5;
+// Two MMA-issuing warps on alternate chunks.  ncu on the one-warp build (profiles/r02_ncu_full_kernels.md): the tensor pipe was
+// busy only while the issuing warp sat blocked on UTCHMMA (37 % of its time) -- the pipe's queue does not cover the warp's own
+// barrier waits and commits, so a second warp that has already passed ITS waits issues the next chunk back to back.
+// Each warp owns one TMEM buffer (chunk parity) and, the ring size being even, two fixed ring slots: a warp only ever waits on
+// its own slots, whose consecutive fills are consecutive phases of their barriers (no phase-parity aliasing, nothing to observe).
+constexpr int kMmaWarps = 2;
+constexpr int kEpiBase = 1 + kMmaWarps;
+constexpr int kThreads = 32 * (kEpiBase + kEpiWarps);      // warp 0: TMA producer, warps 1-2: MMA issuers, warps 3..18: epilogue
+constexpr int kStages = 4;
 constexpr int kTh = 8, kTw = 16;                    // 128 output positions
 constexpr int kCin = 32, kCoutPad = 32;
 constexpr int kABytes = (kTh + 2) * kTw * kCin * 2; // 10 240: one activation box (already a 1 KB multiple)
@@ -144,8 +151,9 @@ conv3d_ds_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp < kEpiBase) {
+        // ===================== MMA issuers: warp 1 + mw issues the chunks with (chunk index & 1) == mw =====================
+        const uint32_t mw = static_cast<uint32_t>(warp - 1);
         constexpr uint32_t pitch = kCin * 2;                                       // 64-byte operand rows, SWIZZLE_64B
         // descriptor high word: SBO (8 rows) | version 1 (bit 46) | swizzle code 4 = 64B (bits 61-63)
         constexpr uint64_t desc_hi = (static_cast<uint64_t>(((8u * pitch) >> 4) | (1u << 14) | (4u << 29))) << 32;
@@ -156,18 +164,19 @@ conv3d_ds_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         const uint32_t w_lo = (smem_u32(wsm) >> 4) | (1u << 16);
         const uint32_t bt16 = static_cast<uint32_t>(p.b_tile_bytes) >> 4;
         mbar_wait(w_bar, 0);                                                       // the resident weights have landed
-        int stage = 0, buf = 0;
-        uint32_t phase = 0, bphase = 0;
+        uint32_t c = 0;                                                            // chunk (= stage) counter over the whole kernel
         for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
             for (int pl = 0; pl < p.depth; ++pl) {
 #pragma unroll
-                for (int dwi = 0; dwi < 3; ++dwi) {
-                    mbar_wait(&tmem_empty[buf], bphase ^ 1);                       // epilogue drained this buffer
-                    mbar_wait(&full_bar[stage], phase);
+                for (int dwi = 0; dwi < 3; ++dwi, ++c) {
+                    if ((c & 1u) != mw) continue;                                  // the other warp's chunk
+                    const uint32_t stage = c & (kStages - 1), buf = c & 1u;        // this warp's own slot / TMEM buffer
+                    mbar_wait(&tmem_empty[buf], ((c >> 1) & 1u) ^ 1u);             // epilogue drained this buffer
+                    mbar_wait(&full_bar[stage], (c >> 2) & 1u);
                     tc_fence_after();
                     if (elect_one_sync()) {
-                        const uint32_t d0 = static_cast<uint32_t>(buf * kBufCols);
-                        const uint32_t a_hi = ring_lo + static_cast<uint32_t>(stage) * (kStageBytes >> 4);
+                        const uint32_t d0 = buf * kBufCols;
+                        const uint32_t a_hi = ring_lo + stage * (kStageBytes >> 4);
                         const uint32_t a_lo = a_hi + (kABytes >> 4);
 #pragma unroll
                         for (int dh = 0; dh < 3; ++dh) {
@@ -184,15 +193,13 @@ conv3d_ds_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                         umma_commit(&tmem_full[buf]);
                     }
                     __syncwarp();
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
-                    if (++buf == kNumBuf) { buf = 0; bphase ^= 1; }
                 }
             }
         }
     } else {
         // ===================== epilogue =====================
         const int q = warp & 3;                          // TMEM lane quarter this warp may access (warp_id % 4)
-        const int g = (warp - 2) >> 2;                   // 8-channel group
+        const int g = (warp - kEpiBase) >> 2;            // 8-channel group
         const int m = q * 32 + lane;
         const int hl = m / kTw, wl = m % kTw;
         const uint32_t lane_base = (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * 8);

@@ -22,6 +22,13 @@ struct rt_conv3d_plan {
     void* ds = nullptr;
     // ---- transposed conv (Cout = 1) + slice + soft-argmax/min as one kernel (deconv_softargmax.cu); set iff desc.fuse_softargmax.
     void* dsa = nullptr;
+    // ---- more than 128 output channels (the 256 / 512-channel layers of the TrailNet classifier): the plan is a list of
+    //      <= 128-channel parts that write their slice of the one output tensor (channel offset out_c_offset of out_c_total);
+    //      the first part's re-layout of a dense input (pack pass) is shared by the others.
+    std::vector<rt_conv3d_plan*> parts;
+    int out_c_total = 0;        // channels of the output tensor this plan writes into (0: its own cout)
+    int out_c_offset = 0;       // first channel this plan writes
+    bool reuse_pack = false;    // the packed activations are already in the workspace (written by an earlier part)
 };
 
 namespace rt {

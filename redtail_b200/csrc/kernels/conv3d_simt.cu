@@ -238,7 +238,37 @@ void host_to_f32(int dtype, const void* src, int64_t count, std::vector<float>& 
 
 extern "C" {
 
+static int conv3d_create_part(const rt_conv3d_desc* d, int out_c_total, int out_c_offset, bool reuse_pack, rt_conv3d_plan** out);
+
 int rt_conv3d_create(const rt_conv3d_desc* d, rt_conv3d_plan** out) {
+    if (!d || !out || !d->weights) return RT_ERR_ARG;
+    // Forward convolutions with more than 128 output channels on the tensor-core path: <= 128-channel parts (conv3d_internal.h).
+    if (!d->transposed && d->k > 128 && d->precision != RT_PREC_SIMT && !d->fuse_softargmax && d->k % 8 == 0) {
+        rt_conv3d_plan* top = new rt_conv3d_plan();
+        top->desc = *d;
+        top->desc.weights = nullptr; top->desc.bias = nullptr;
+        top->cout = d->k; top->cin = d->c;
+        top->out_planes = d->out_dims[1];
+        const size_t es = d->weights_dtype == RT_F16 ? 2 : 4;
+        const size_t per_k = static_cast<size_t>(d->v) * d->c * d->r * d->s;
+        for (int k0 = 0; k0 < d->k; k0 += 128) {
+            rt_conv3d_desc pd = *d;
+            pd.k = d->k - k0 < 128 ? d->k - k0 : 128;
+            pd.out_dims[0] = pd.k;
+            pd.weights = static_cast<const char*>(d->weights) + static_cast<size_t>(k0) * per_k * es;
+            pd.bias = d->bias ? static_cast<const char*>(d->bias) + static_cast<size_t>(k0) * es : nullptr;
+            rt_conv3d_plan* part = nullptr;
+            const int rc = conv3d_create_part(&pd, d->k, k0, k0 > 0, &part);
+            if (rc != RT_OK) { rt_conv3d_destroy(top); return rc; }
+            top->parts.push_back(part);
+        }
+        *out = top;
+        return RT_OK;
+    }
+    return conv3d_create_part(d, 0, 0, false, out);
+}
+
+static int conv3d_create_part(const rt_conv3d_desc* d, int out_c_total, int out_c_offset, bool reuse_pack, rt_conv3d_plan** out) {
     if (!d || !out || !d->weights) return RT_ERR_ARG;
     if (d->k <= 0 || d->v <= 0 || d->c <= 0 || d->r <= 0 || d->s <= 0) return RT_ERR_ARG;
     for (int i = 0; i < 3; ++i)
@@ -265,6 +295,7 @@ int rt_conv3d_create(const rt_conv3d_desc* d, rt_conv3d_plan** out) {
     p->desc = *d;
     p->desc.weights = nullptr;
     p->desc.bias = nullptr;
+    p->out_c_total = out_c_total; p->out_c_offset = out_c_offset; p->reuse_pack = reuse_pack;
     p->out_planes = d->transposed ? d->out_dims[0] - d->slice_d : d->out_dims[1];
     p->cout = d->transposed ? d->c : d->k;
     p->cin = d->transposed ? d->k : d->c;
@@ -309,6 +340,7 @@ int rt_conv3d_create(const rt_conv3d_desc* d, rt_conv3d_plan** out) {
         *out = p;
         return RT_OK;
     }
+    if (d->precision == RT_PREC_SIMT && out_c_total != 0) { rt_conv3d_destroy(p); return RT_ERR_UNSUPPORTED; }
     if (d->precision != RT_PREC_SIMT) {
         const int rc = tc_plan_init(p, w, b);
         if (rc != RT_OK) {           // no silent downgrade of a requested tensor-core precision
@@ -335,6 +367,7 @@ int rt_conv3d_tc_supported(const rt_conv3d_desc* d) {
 
 void rt_conv3d_destroy(rt_conv3d_plan* p) {
     if (!p) return;
+    for (rt_conv3d_plan* part : p->parts) rt_conv3d_destroy(part);
     tc_plan_destroy(p);
     ds_plan_destroy(p);
     dsa_plan_destroy(p);
@@ -344,6 +377,7 @@ void rt_conv3d_destroy(rt_conv3d_plan* p) {
 }
 
 size_t rt_conv3d_workspace_size(const rt_conv3d_plan* p, int max_batch) {
+    if (p && !p->parts.empty()) return rt_conv3d_workspace_size(p->parts[0], max_batch);    // same input, same packed planes
     if (!p || !p->tc) return 0;
     return tc_workspace_size(p, max_batch);
 }
@@ -352,6 +386,13 @@ int rt_conv3d_enqueue(const rt_conv3d_plan* p, int n, const void* x, const void*
                       void* stream) {
     if (!p || !x || !y || n < 0) return RT_ERR_ARG;
     if (n == 0) return RT_OK;
+    if (!p->parts.empty()) {
+        for (const rt_conv3d_plan* part : p->parts) {
+            const int rc = rt_conv3d_enqueue(part, n, x, skip, y, workspace, stream);
+            if (rc != RT_OK) return rc;
+        }
+        return RT_OK;
+    }
     if (p->dsa) return skip ? RT_ERR_ARG : dsa_enqueue(p, n, x, y, as_stream(stream));
     if (p->ds && !skip) return ds_conv3d_enqueue(p, n, x, y, as_stream(stream));
     if (p->tc)

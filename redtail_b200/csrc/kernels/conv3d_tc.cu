@@ -714,7 +714,8 @@ bool tc_shape_supported(const rt_conv3d_desc& d) {
     // too); a split16 input is consumed in place and must already have a block-sized channel count.
     if (cin < 1) return false;
     if (d.in_layout == RT_LAYOUT_SPLIT16 && tc_padded_cin(cin) != cin) return false;
-    if (cout > 128 || cout < 1) return false;
+    if (cout < 1) return false;
+    if (cout > 128 && (d.transposed || cout % 8 != 0)) return false;      // > 128: <= 128-channel parts (forward convs, rt_conv3d_create)
     if (d.v > 3 || d.r > 3 || d.s > 3) return false;
     for (int i = 0; i < 3; ++i)
         if (d.stride[i] > 2 || d.stride[i] < 1) return false;
@@ -730,6 +731,9 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     const int cin = tc_padded_cin(cin_src);            // zero-padded by the pack pass (weights of the padding are zero too)
     if (!tc_shape_supported(d)) return RT_ERR_UNSUPPORTED;
     const bool out_split = d.out_layout == RT_LAYOUT_SPLIT16;
+    // This plan may be one <= 128-channel part of a wider convolution: it then writes channels [coff, coff + cout) of ctot.
+    const int ctot = plan->out_c_total > 0 ? plan->out_c_total : cout, coff = plan->out_c_total > 0 ? plan->out_c_offset : 0;
+    if (tr && plan->out_c_total > 0) return RT_ERR_UNSUPPORTED;
     // Channels per parity class (power of two) and which stride-2 output parities are merged into GEMM-N.
     int cpc = 1;
     while (cpc < cout) cpc *= 2;
@@ -790,9 +794,9 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
         out_ext[0] = d.out_dims[1]; out_ext[1] = d.out_dims[2]; out_ext[2] = d.out_dims[3];
         for (int i = 0; i < 3; ++i) { p.in_s[i] = d.stride[i]; p.out_s[i] = 1; }
         const long long plane = static_cast<long long>(out_ext[1]) * out_ext[2];
-        if (d.out_transposed) { p.out_sd = cout * plane; p.out_sc = plane; }          // [Do,K,Ho,Wo]
+        if (d.out_transposed) { p.out_sd = ctot * plane; p.out_sc = plane; }          // [Do,K,Ho,Wo]
         else { p.out_sc = out_ext[0] * plane; p.out_sd = plane; }                       // [K,Do,Ho,Wo]
-        p.out_sn = static_cast<long long>(cout) * out_ext[0] * plane;
+        p.out_sn = static_cast<long long>(ctot) * out_ext[0] * plane;
     } else {
         t->in_d = d.in_dims[1]; t->in_h = d.in_dims[2]; t->in_w = d.in_dims[3];
         t->in_sc = static_cast<long long>(t->in_d) * t->in_h * t->in_w;  // input [K,D,H,W]
@@ -992,9 +996,9 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     }
     // Output addressing + device column table.
     p.out_split = out_split ? 1 : 0;
-    p.out_c = cout;
+    p.out_c = ctot;
     if (out_split) {
-        const long long plane_elems = static_cast<long long>(p.out_d) * p.out_h * p.out_w * cout;
+        const long long plane_elems = static_cast<long long>(p.out_d) * p.out_h * p.out_w * ctot;
         p.out_sn = 2 * plane_elems;          // halves per sample: hi plane + lo plane
         p.out_lo = plane_elems;
     }
@@ -1005,8 +1009,8 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
             ColInfo ci2;
             ci2.ch = cd.c;
             ci2.pidx = cd.valid ? cd.pd * 4 + cd.ph * 2 + cd.pw : 8;
-            ci2.off = out_split ? ((static_cast<long long>(cd.pd) * p.out_h + cd.ph) * p.out_w + cd.pw) * cout + cd.c
-                                : cd.pd * p.out_sd + cd.c * p.out_sc + static_cast<long long>(cd.ph) * p.out_w + cd.pw;
+            ci2.off = out_split ? ((static_cast<long long>(cd.pd) * p.out_h + cd.ph) * p.out_w + cd.pw) * ctot + cd.c + coff
+                                : cd.pd * p.out_sd + (cd.c + coff) * p.out_sc + static_cast<long long>(cd.ph) * p.out_w + cd.pw;
             tab[col] = ci2;
         }
         if (cudaMalloc(&t->d_cols, tab.size() * sizeof(ColInfo)) != cudaSuccess ||
@@ -1090,12 +1094,24 @@ int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const f
     } else {
         __half* whi = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
         if (static_cast<long long>(n) * t->in_d > 65535 || t->in_h > 65535) return RT_ERR_UNSUPPORTED;
-        dim3 grid((t->in_w + 63) / 64, t->in_h, n * t->in_d);
-        const size_t sm = static_cast<size_t>(t->cin) * 65 * sizeof(float);
-        pack_split_kernel<<<grid, 256, sm, s>>>(x, whi, whi + t->in_elems, t->in_d, t->cin_src, t->cin, t->in_h, t->in_w, t->in_sn,
-                                                t->in_sd, t->in_sc, static_cast<long long>(2 * t->in_elems));
-        note_launch("conv3d_pack_split");
-        RT_CHECK_LAUNCH();
+        if (!plan->reuse_pack) {        // parts 1.. of a > 128-channel convolution read the planes part 0 has just written
+            dim3 grid((t->in_w + 63) / 64, t->in_h, n * t->in_d);
+            const size_t sm = static_cast<size_t>(t->cin) * 65 * sizeof(float);
+            if (sm > 48 * 1024) {               // 256 / 512-channel inputs (TrailNet): the transpose tile needs the opt-in limit
+                static bool pack_attr[64] = {};
+                int dev_ = 0;
+                RT_CUDA(cudaGetDevice(&dev_));
+                if (sm > 227 * 1024) return RT_ERR_UNSUPPORTED;
+                if (dev_ < 0 || dev_ >= 64 || !pack_attr[dev_]) {
+                    RT_CUDA(cudaFuncSetAttribute(pack_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                    if (dev_ >= 0 && dev_ < 64) pack_attr[dev_] = true;
+                }
+            }
+            pack_split_kernel<<<grid, 256, sm, s>>>(x, whi, whi + t->in_elems, t->in_d, t->cin_src, t->cin, t->in_h, t->in_w, t->in_sn,
+                                                    t->in_sd, t->in_sc, static_cast<long long>(2 * t->in_elems));
+            note_launch("conv3d_pack_split");
+            RT_CHECK_LAUNCH();
+        }
         hi = whi;
     }
     const __half* lo = hi + t->in_elems;
