@@ -109,7 +109,7 @@ struct TcParams {
     int out_split;           // 1: y (and skip) are RT_LAYOUT_SPLIT16, 0: dense fp32
     int dbg;                 // timing experiments only (REDTAIL_TC_DEBUG bit mask; results are garbage): 1 = epilogue skips the
                              // tcgen05.ld drains, 2 = no MMAs are issued, 4 = the producer moves no data, 8 = no output phase (bias/ELU/stores);
-                             // A/B switches with correct results: 16 = L2 prefetch of the skip tensor at tile start, 32 = skip vectors loaded per batch
+                             // A/B switches with correct results: 16 / 64 = L2 / L1 prefetch of the skip tensor at tile start, 32 = skip vectors loaded per batch
     int out_c;               // channels of the output tensor (split16 addressing)
     long long out_lo;        // split16: offset of the lo plane, in halves
     int interleave;          // > 0 (experiment, REDTAIL_TC_INTERLEAVE=1): job index = tile * nclasses + class over the common tile
@@ -498,7 +498,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             // Experiment (REDTAIL_TC_DEBUG=16): ask L2 for this tile's skip lines at the start of the tile.  Measured on NVSmall:
             // deconv3D_2 0.514 -> 0.568 ms, deconv3D_1 0.182 -> 0.196 ms WITH the prefetch -- the extra requests cost more than
             // the (already overlapped) latency they hide; off by default.
-            if (skip != nullptr && p.out_split && (p.dbg & 16)) {
+            if (skip != nullptr && p.out_split && (p.dbg & (16 | 64))) {
                 const __half* sk16 = reinterpret_cast<const __half*>(skip);
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
@@ -511,8 +511,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                             const ColInfo c0 = s_col[col0 + k0];
                             const int q8 = c0.pidx;
                             if (q8 < 8 && bd + (q8 >> 2) < p.out_d && bh + ((q8 >> 1) & 1) < p.out_h && bw + (q8 & 1) < p.out_w) {
-                                prefetch_l2(sk16 + rowbase + c0.off);
-                                prefetch_l2(sk16 + p.out_lo + rowbase + c0.off);
+                                if (p.dbg & 64) { prefetch_l1(sk16 + rowbase + c0.off); prefetch_l1(sk16 + p.out_lo + rowbase + c0.off); }
+                                else { prefetch_l2(sk16 + rowbase + c0.off); prefetch_l2(sk16 + p.out_lo + rowbase + c0.off); }
                             }
                         }
                     }

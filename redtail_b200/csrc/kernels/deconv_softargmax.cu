@@ -28,8 +28,10 @@ namespace rt {
 namespace {
 
 constexpr int kEpiWarps = 16;
-constexpr int kThreads = 32 * (2 + kEpiWarps);
-constexpr int kStages = 5;
+constexpr int kMmaWarps = 2;                         // two issuing warps on alternate planes, fixed ring slots (see conv3d_ds.cu)
+constexpr int kEpiBase = 1 + kMmaWarps;
+constexpr int kThreads = 32 * (kEpiBase + kEpiWarps);
+constexpr int kStages = 4;
 constexpr int kTh = 8, kTw = 16;
 constexpr int kCin = 32;
 constexpr int kBox = (kTh + 1) * kTw * kCin * 2;     // 9 216 B: one activation box
@@ -123,8 +125,9 @@ deconv_softargmax_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp < kEpiBase) {
+        // ===================== MMA issuers: warp 1 + mw issues the planes with (plane counter & 1) == mw =====================
+        const uint32_t mw = static_cast<uint32_t>(warp - 1);
         constexpr uint32_t pitch = kCin * 2;                                       // 64-byte operand rows, SWIZZLE_64B
         constexpr uint64_t desc_hi = (static_cast<uint64_t>(((8u * pitch) >> 4) | (1u << 14) | (4u << 29))) << 32;
         constexpr uint32_t idesc1 = umma_idesc_f16(128, WLO ? 32 : 16);
@@ -133,16 +136,17 @@ deconv_softargmax_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         const uint32_t ring_lo = (smem_u32(ring) >> 4) | (1u << 16);
         const uint32_t w_lo = (smem_u32(wsm) >> 4) | (1u << 16);
         mbar_wait(w_bar, 0);
-        int stage = 0, buf = 0;
-        uint32_t phase = 0, bphase = 0;
+        uint32_t c = 0;                                                            // plane (= stage = chunk) counter over the whole kernel
         for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
-            for (int pl = 0; pl < p.depth; ++pl) {
-                mbar_wait(&tmem_empty[buf], bphase ^ 1);
-                mbar_wait(&full_bar[stage], phase);
+            for (int pl = 0; pl < p.depth; ++pl, ++c) {
+                if ((c & 1u) != mw) continue;
+                const uint32_t stage = c & (kStages - 1), buf = c & (kNumBuf - 1);    // even ring / buffer counts: fixed ownership
+                mbar_wait(&tmem_empty[buf], ((c / kNumBuf) & 1u) ^ 1u);
+                mbar_wait(&full_bar[stage], (c / kStages) & 1u);
                 tc_fence_after();
                 if (elect_one_sync()) {
-                    const uint32_t d0 = static_cast<uint32_t>(buf * kBufCols);
-                    const uint32_t st = ring_lo + static_cast<uint32_t>(stage) * (kStageBytes >> 4);
+                    const uint32_t d0 = buf * kBufCols;
+                    const uint32_t st = ring_lo + stage * (kStageBytes >> 4);
 #pragma unroll
                     for (int ow = 0; ow < 2; ++ow) {
 #pragma unroll
@@ -162,14 +166,12 @@ deconv_softargmax_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                     umma_commit(&tmem_full[buf]);
                 }
                 __syncwarp();
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
-                if (++buf == kNumBuf) { buf = 0; bphase ^= 1; }
             }
         }
     } else {
         // ===================== epilogue: one output pixel (ph, pw) of one lattice position per thread =====================
         const int q = warp & 3;                          // TMEM lane quarter
-        const int e = (warp - 2) >> 2;                   // output parity index ph * 2 + pw
+        const int e = (warp - kEpiBase) >> 2;            // output parity index ph * 2 + pw
         const int m = q * 32 + lane;
         const int hl = m / kTw, wl = m % kTw;
         const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
