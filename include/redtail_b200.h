@@ -123,6 +123,9 @@ typedef struct {
     int fuse_softargmax;     /* transposed, C == 1 only: 0 none, 1 soft-argmin, 2 soft-argmax over the (sliced) output planes
                                 (fuses SoftargmaxPlugin, lib/softargmax_plugin.cpp:167-205): y is then [n,Hx,Wx] fp32 and the
                                 [Dx,1,Hx,Wx] volume is never written.  Needs RT_PREC_FP32, a split16 input, K == 32.       */
+    const float* act_params; /* conv only, tensor-core precisions: host array [4][K] = s1, b1, s2, b2 or NULL.  Applied after bias and
+                                skip:  y = max(v * s1[k] + b1[k], 0) * s2[k] + b2[k]  -- the S-ReLU chain Scale -> ReLU -> Scale of the
+                                TrailNet model (TrailNet_SResNet-18.prototxt:54-105) fused into the convolution.               */
 } rt_conv3d_desc;
 
 int  rt_conv3d_create(const rt_conv3d_desc* desc, rt_conv3d_plan** plan);   /* repacks + uploads weights        */
@@ -190,6 +193,10 @@ int rt_pool2d(const void* x, void* y, int n, int c, int h, int w, int out_h, int
               void* stream);
 /* InnerProduct: y[n,m] = b[m] + sum_k x[n,k] W[m,k]  (W, b device fp32; b may be NULL). */
 int rt_fully_connected(const void* x, const float* w, const float* b, void* y, int n, int k, int m, void* stream);
+/* im2col for 2-D filters larger than 3x3 (TrailNet conv1, 7x7 stride 2): x [n,c,h,w] fp32 -> RT_LAYOUT_SPLIT16 [n][hi|lo][1][out_h][out_w][kp],
+ * K index = (ci*r + ri)*s + si (KCRS weight order), zero for K >= c*r*s; the convolution is then 1x1 over kp channels on tcgen05. */
+int rt_im2col_split16(const void* x, void* y, int n, int c, int h, int w, int r, int s, int stride, int pad, int out_h, int out_w,
+                      int kp, void* stream);
 /* Softmax over the channel dimension of [n,c,inner], max-subtracted. */
 int rt_softmax_channels(const void* x, void* y, int n, int c, int64_t inner, void* stream);
 

@@ -21,7 +21,7 @@ class Conv3dDesc(C.Structure):
                 ("stride", C.c_int * 3), ("pad", C.c_int * 3), ("in_dims", C.c_int * 4), ("out_dims", C.c_int * 4),
                 ("weights_dtype", C.c_int), ("weights", C.c_void_p), ("bias", C.c_void_p), ("precision", C.c_int),
                 ("fuse_elu", C.c_int), ("out_transposed", C.c_int), ("slice_d", C.c_int),
-                ("in_layout", C.c_int), ("out_layout", C.c_int), ("pad_end_d", C.c_int), ("fuse_softargmax", C.c_int)]
+                ("in_layout", C.c_int), ("out_layout", C.c_int), ("pad_end_d", C.c_int), ("fuse_softargmax", C.c_int), ("act_params", C.c_void_p)]
 
 
 class Conv2dDesc(C.Structure):
@@ -53,6 +53,7 @@ KERNEL_API = {
     "rt_pool2d": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rt_fully_connected": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "rt_softmax_channels": (_I, [_P, _P, _I, _I, _L, _P]),
+    "rt_im2col_split16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rt_cost_volume": (_I, [_I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rt_corr_cost_volume": (_I, [_I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rt_elu": (_I, [_I, _P, _P, _L, _P]),

@@ -479,6 +479,7 @@ struct TensorSlot {
     int pair_of = -1;          // siamese partner: stored right behind tensor `pair_of` (at + batch * elems) so that one launch
                                // of batch 2N covers both towers
     bool has_partner = false;  // some tensor names this one as its pair_of: the allocation is twice the size
+    bool forced_split = false; // engine-made tensor that only exists in RT_LAYOUT_SPLIT16 (the im2col matrix of a large-filter conv)
     size_t offset = 0;         // arena offset (bytes) when neither binding nor alias
     int first = -1, last = -1; // step liveness
     bool used = false;
@@ -615,6 +616,7 @@ public:
     std::vector<rt_cvconv_plan*> cvconv_plans_;
     std::vector<std::unique_ptr<ConvStep>> conv_steps_;
     std::vector<void*> dev_blobs_;       // per-channel scale / shift arrays and fully-connected weights of the native layers
+    std::vector<std::vector<float>> host_blobs_;   // re-laid-out host weights the conv descriptors point to until the plans exist
 
     // Host weights (fp32 or fp16) -> device fp32 array of `count` elements (`fill` where the layer has none); nullptr on failure.
     float* deviceArray(const Weights& w, int64_t count, float fill)
@@ -803,6 +805,7 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                 cd.bias = d.bw.count > 0 ? d.bw.values : nullptr;
                 TensorImpl* out = d.out[0];
                 int nxt = fusion ? soleConsumer(out) : -1;
+                int im2col_in = -1;                  // >= 0: the conv reads this engine-made im2col matrix instead of its input
                 // A 2-D (transposed) convolution is a 3-D one with V = D = 1 ([K,1,H,W] == [K,H,W]): the tower convs, the
                 // ResNet18_2D encoder / decoder and its deconvolutions run on the same tcgen05 implicit-GEMM kernel as the 3-D
                 // stack, with its epilogue fusions (+skip, ELU).  Channel counts that are not a K-block multiple (the 33-channel
@@ -828,10 +831,82 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                 c3.weights_dtype = cd.weights_dtype; c3.weights = cd.weights; c3.bias = cd.bias;
                 c3.precision = pe2 && !strcmp(pe2, "fp16") ? RT_PREC_FP16 : RT_PREC_FP32;
                 const char* tw_env = getenv("REDTAIL_ENGINE_TOWER_SPLIT16");
-                const bool tc2 = fusion && !simt_only && !(tw_env && tw_env[0] == '0') && rt_conv3d_tc_supported(&c3) == 1;
+                bool tc2 = fusion && !simt_only && !(tw_env && tw_env[0] == '0') && rt_conv3d_tc_supported(&c3) == 1;
+                // A forward convolution with a filter larger than 3x3 and a GEMM-K worth the trip (TrailNet conv1: 7x7 stride 2 over 3
+                // channels, K = 147; ros/packages/caffe_ros + TrailNet_SResNet-18.prototxt:31-53) runs as im2col + a 1x1 convolution
+                // over K "channels" on the tcgen05 kernel: 30 % of the TrailNet step on the CUDA-core kernel otherwise.  The 5x5 first
+                // tower layer of the stereo nets (K = 75, 0.06 ms) stays on CUDA cores.
+                const int gemm_k = cd.cin * cd.r * cd.s;
+                const char* s16_env = getenv("REDTAIL_ENGINE_SPLIT16");
+                const char* i2c_env = getenv("REDTAIL_ENGINE_IM2COL");
+                if (!tc2 && !tr2 && fusion && !simt_only && (cd.r > 3 || cd.s > 3) && gemm_k > 96 && gemm_k <= 512 &&
+                    !(s16_env && s16_env[0] == '0') && !(i2c_env && i2c_env[0] == '0') && cd.stride[0] == cd.stride[1] && cd.pad[0] == cd.pad[1]) {
+                    const int kp = (gemm_k + 63) / 64 * 64;
+                    // weights [cout][cin*r*s] -> [cout][kp], zero padded, fp32 (the engine owns the buffer)
+                    host_blobs_.emplace_back(static_cast<size_t>(cd.cout) * kp, 0.f);
+                    std::vector<float>& wb = host_blobs_.back();
+                    for (int k = 0; k < cd.cout; ++k)
+                        for (int j = 0; j < gemm_k; ++j) {
+                            const size_t src = static_cast<size_t>(k) * gemm_k + j;
+                            float v;
+                            if (d.kw.type == DataType::kHALF) {
+                                const uint16_t hb = static_cast<const uint16_t*>(d.kw.values)[src];
+                                const uint32_t sign = (hb >> 15) & 1u, ex = (hb >> 10) & 31u, man = hb & 1023u;
+                                v = ex == 0 ? ldexpf(static_cast<float>(man), -24) : ex == 31 ? (man ? NAN : INFINITY) : ldexpf(static_cast<float>(man | 1024u), static_cast<int>(ex) - 25);
+                                if (sign) v = -v;
+                            } else v = static_cast<const float*>(d.kw.values)[src];
+                            wb[static_cast<size_t>(k) * kp + j] = v;
+                        }
+                    rt_conv3d_desc g{};
+                    g.k = cd.cout; g.v = 1; g.c = kp; g.r = 1; g.s = 1;
+                    for (int i = 0; i < 3; ++i) { g.stride[i] = 1; g.pad[i] = 0; }
+                    g.in_dims[0] = 1; g.in_dims[1] = kp; g.in_dims[2] = ho2; g.in_dims[3] = wo2;
+                    g.out_dims[0] = cd.cout; g.out_dims[1] = 1; g.out_dims[2] = ho2; g.out_dims[3] = wo2;
+                    g.weights_dtype = RT_F32; g.weights = wb.data();
+                    g.bias = cd.bias; g.precision = c3.precision;
+                    if (cd.bias && cd.weights_dtype == RT_F16) {         // bias in the same dtype as the (now fp32) weights
+                        host_blobs_.emplace_back(static_cast<size_t>(cd.cout), 0.f);
+                        const uint16_t* hb = static_cast<const uint16_t*>(cd.bias);
+                        for (int k = 0; k < cd.cout; ++k) {
+                            const uint32_t sign = (hb[k] >> 15) & 1u, ex = (hb[k] >> 10) & 31u, man = hb[k] & 1023u;
+                            float v = ex == 0 ? ldexpf(static_cast<float>(man), -24) : ex == 31 ? (man ? NAN : INFINITY) : ldexpf(static_cast<float>(man | 1024u), static_cast<int>(ex) - 25);
+                            host_blobs_.back()[k] = sign ? -v : v;
+                        }
+                        g.bias = host_blobs_.back().data();
+                    }
+                    g.in_layout = RT_LAYOUT_SPLIT16;
+                    if (rt_conv3d_tc_supported(&g) == 1) {
+                        // the im2col matrix: an engine-made tensor that only exists in the split16 layout
+                        TensorSlot ms;
+                        ms.name = d.name + "_im2col";
+                        ms.dims = DimsCHW(kp, ho2, wo2);
+                        ms.elems = static_cast<size_t>(kp) * ho2 * wo2;
+                        ms.forced_split = true;
+                        const int mid = static_cast<int>(slots_.size());
+                        slots_.push_back(ms);
+                        Step im;
+                        im.name = d.name + "_im2col";
+                        im.in.push_back(d.in[0]->id);
+                        im.out.push_back(mid);
+                        const int xin = d.in[0]->id, cin_ = cd.cin, ih = cd.in_h, iw = cd.in_w, fr = cd.r, fs = cd.s, fst = cd.stride[0], fpd = cd.pad[0];
+                        im.run = [=](int batch, const std::function<void*(int)>& ptr, void*, cudaStream_t s) {
+                            return rt_im2col_split16(ptr(xin), ptr(mid), batch, cin_, ih, iw, fr, fs, fst, fpd, ho2, wo2, kp, s);
+                        };
+                        steps_.push_back(std::move(im));
+                        g.in_layout = RT_LAYOUT_DENSE;        // decided (to split16) by the layout pass
+                        c3 = g;
+                        st.in.clear();
+                        st.in.push_back(mid);
+                        im2col_in = mid;
+                        tc2 = true;
+                    }
+                }
                 int skip2 = -1;
-                if (tc2 && tr2 && nxt >= 0 && net.layers_[nxt]->d.kind == LKind::kEltwise) {
-                    // deconv -> + skip (kSUM) [-> ELU]: the ResNet18_2D decoder (resnet18_2D_513x257_net.cpp:700-760)
+                const char* act_env = getenv("REDTAIL_ENGINE_ACT_FUSION");
+                const bool act_fusion = !(act_env && act_env[0] == '0');
+                if (tc2 && (tr2 || act_fusion) && nxt >= 0 && net.layers_[nxt]->d.kind == LKind::kEltwise) {
+                    // deconv -> + skip (kSUM) [-> ELU]: the ResNet18_2D decoder (resnet18_2D_513x257_net.cpp:700-760);
+                    // conv -> + shortcut (kSUM) [-> S-ReLU]: the residual blocks of TrailNet (TrailNet_SResNet-18.prototxt:217-278)
                     LayerData& e = net.layers_[nxt]->d;
                     TensorImpl* other = e.in[0] == out ? e.in[1] : e.in[0];
                     if (other != out && (other->is_input || (other->producer >= 0 && other->producer < li))) {
@@ -846,13 +921,46 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                     out = net.layers_[nxt]->d.out[0];
                     st.name += " + " + net.layers_[nxt]->d.name;
                 }
+                // conv [+ shortcut] -> Scale(per channel) -> ReLU -> Scale(per channel): the S-ReLU of TrailNet in the epilogue
+                if (tc2 && !tr2 && act_fusion && !cd.fuse_elu && nxt >= 0 && net.layers_[nxt]->d.kind == LKind::kScale &&
+                    net.layers_[nxt]->d.smode == ScaleMode::kCHANNEL && net.layers_[nxt]->d.power.count == 0) {
+                    const int n0 = nxt, n1 = soleConsumer(net.layers_[n0]->d.out[0]);
+                    const int n2 = n1 >= 0 && net.layers_[n1]->d.kind == LKind::kActivation && net.layers_[n1]->d.act == ActivationType::kRELU
+                                       ? soleConsumer(net.layers_[n1]->d.out[0]) : -1;
+                    if (n2 >= 0 && net.layers_[n2]->d.kind == LKind::kScale && net.layers_[n2]->d.smode == ScaleMode::kCHANNEL &&
+                        net.layers_[n2]->d.power.count == 0) {
+                        const int co = cd.cout;
+                        host_blobs_.emplace_back(static_cast<size_t>(4) * co, 0.f);
+                        std::vector<float>& ap = host_blobs_.back();
+                        auto fill = [&](int row, const Weights& w, float dflt) {
+                            for (int k = 0; k < co; ++k) {
+                                float v = dflt;
+                                if (w.count == co && w.values) {
+                                    if (w.type == DataType::kHALF) {
+                                        const uint16_t hb = static_cast<const uint16_t*>(w.values)[k];
+                                        const uint32_t sign = (hb >> 15) & 1u, ex = (hb >> 10) & 31u, man = hb & 1023u;
+                                        v = ex == 0 ? ldexpf(static_cast<float>(man), -24) : ex == 31 ? (man ? NAN : INFINITY) : ldexpf(static_cast<float>(man | 1024u), static_cast<int>(ex) - 25);
+                                        if (sign) v = -v;
+                                    } else v = static_cast<const float*>(w.values)[k];
+                                }
+                                ap[static_cast<size_t>(row) * co + k] = v;
+                            }
+                        };
+                        fill(0, net.layers_[n0]->d.scale, 1.f); fill(1, net.layers_[n0]->d.shift, 0.f);
+                        fill(2, net.layers_[n2]->d.scale, 1.f); fill(3, net.layers_[n2]->d.shift, 0.f);
+                        c3.act_params = ap.data();
+                        done[n0] = done[n1] = done[n2] = true;
+                        out = net.layers_[n2]->d.out[0];
+                        st.name += " + " + net.layers_[n0]->d.name + " + " + net.layers_[n1]->d.name + " + " + net.layers_[n2]->d.name;
+                    }
+                }
                 if (tc2) {
                     c3.fuse_elu = cd.fuse_elu;
                     // Deferred like the 3-D layers: the layout pass may keep the activations between consecutive convolutions
                     // in RT_LAYOUT_SPLIT16 (no re-layout pass in front of the next conv).
                     conv_steps_.emplace_back(new ConvStep());
                     ConvStep* cs = conv_steps_.back().get();
-                    cs->desc = c3; cs->in_id = d.in[0]->id; cs->out_id = out->id; cs->skip_id = skip2; cs->name = d.name;
+                    cs->desc = c3; cs->in_id = im2col_in >= 0 ? im2col_in : d.in[0]->id; cs->out_id = out->id; cs->skip_id = skip2; cs->name = d.name;
                     if (skip2 >= 0) st.in.push_back(skip2);
                     st.out.push_back(out->id);
                     st.conv = cs;
@@ -1346,7 +1454,7 @@ bool EngineImpl::assignLayoutsAndCreatePlans(bool fusion)
             const bool conv_prod = ps.conv && (ps.conv->cvfused ? cvSplitOk(ps.conv) : tcOk(ps.conv, RT_LAYOUT_DENSE, RT_LAYOUT_SPLIT16));
             const bool cv_prod = ps.costvol_d > 0 && ps.costvol_c % 8 == 0;
             const bool tr_prod = ps.is_transform;              // decided through its input below
-            split[t] = (conv_prod || cv_prod || tr_prod) ? 1 : 0;
+            split[t] = (conv_prod || cv_prod || tr_prod || slots_[t].forced_split) ? 1 : 0;
         }
         // ... then demote until every constraint holds.
         for (bool changed = true; changed;) {
@@ -1395,6 +1503,8 @@ bool EngineImpl::assignLayoutsAndCreatePlans(bool fusion)
             sm.dropped = true;
         }
     }
+    for (int t = 0; t < nt; ++t)
+        if (slots_[t].forced_split && !split[t]) return fail(slots_[t].name + ": the im2col matrix needs the split16 layout (REDTAIL_ENGINE_IM2COL=0 keeps the CUDA-core kernel)");
     int nsplit = 0;
     for (int si = 0; si < ns; ++si) {
         Step& st = steps_[si];
@@ -1460,7 +1570,8 @@ void EngineImpl::pairSiameseSteps()
         for (int i = 0; i < 4; ++i) if (a.in_dims[i] != b.in_dims[i] || a.out_dims[i] != b.out_dims[i]) return false;
         if (a.weights_dtype != b.weights_dtype || a.precision != b.precision || a.fuse_elu != b.fuse_elu ||
             a.out_transposed != b.out_transposed || a.slice_d != b.slice_d || a.in_layout != b.in_layout ||
-            a.out_layout != b.out_layout || a.pad_end_d != b.pad_end_d || (a.bias == nullptr) != (b.bias == nullptr))
+            a.out_layout != b.out_layout || a.pad_end_d != b.pad_end_d || (a.bias == nullptr) != (b.bias == nullptr) ||
+            a.fuse_softargmax != b.fuse_softargmax || a.act_params != nullptr || b.act_params != nullptr)
             return false;
         const size_t es = a.weights_dtype == RT_F16 ? 2 : 4;
         const size_t wn = static_cast<size_t>(a.k) * a.v * a.c * a.r * a.s;

@@ -91,6 +91,38 @@ softmax_channels_kernel(const float* __restrict__ x, float* __restrict__ y, int 
     }
 }
 
+// im2col for 2-D convolutions with filters larger than 3x3 (TrailNet conv1: 7x7, stride 2, 3 channels): x [n,c,h,w] fp32 ->
+// RT_LAYOUT_SPLIT16 matrix [n][hi|lo][1][ho][wo][kp] with K index = (ci * r + ri) * s + si (the KCRS order of the weights), zero
+// beyond c*r*s.  The convolution itself is then a 1x1 convolution over kp "channels" on the tcgen05 kernel.
+// One thread = one output position x 8 consecutive K (one 16-byte vector per fp16 plane); K groups fastest -> coalesced stores.
+__global__ void __launch_bounds__(256)
+im2col_split16_kernel(const float* __restrict__ x, __half* __restrict__ y, int c, int h, int w, int r, int s, int stride, int pad,
+                      int ho, int wo, int kp, int64_t total) {
+    const int groups = kp >> 3, krs = c * r * s;
+    const int64_t plane = static_cast<int64_t>(ho) * wo * kp;          // halves of one fp16 plane per sample
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % groups);
+        const int64_t pos = i / groups;
+        const int ox = static_cast<int>(pos % wo), oy = static_cast<int>((pos / wo) % ho);
+        const int64_t n = pos / (static_cast<int64_t>(wo) * ho);
+        const float* xn = x + n * c * h * w;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = g * 8 + j;
+            float val = 0.f;
+            if (k < krs) {
+                const int si = k % s, ri = (k / s) % r, ci = k / (r * s);
+                const int iy = oy * stride - pad + ri, ix = ox * stride - pad + si;
+                if (iy >= 0 && iy < h && ix >= 0 && ix < w) val = __ldg(xn + (static_cast<int64_t>(ci) * h + iy) * w + ix);
+            }
+            v[j] = val;
+        }
+        const int64_t o = n * 2 * plane + (static_cast<int64_t>(oy) * wo + ox) * kp + g * 8;
+        split_store8(v, y + o, y + plane + o);
+    }
+}
+
 inline int grid_for(int64_t total) {
     const int64_t blocks = ceil_div(total, 256);
     const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
@@ -163,6 +195,19 @@ extern "C" int rt_softmax_channels(const void* x, void* y, int n, int c, int64_t
     if (total == 0) return RT_OK;
     softmax_channels_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(static_cast<const float*>(x), static_cast<float*>(y), c, inner, total);
     note_launch("softmax_channels");
+    RT_CHECK_LAUNCH();
+    return RT_OK;
+}
+
+extern "C" int rt_im2col_split16(const void* x, void* y, int n, int c, int h, int w, int r, int s, int stride, int pad, int out_h, int out_w,
+                                 int kp, void* stream) {
+    if (!x || !y || n < 0 || c <= 0 || h <= 0 || w <= 0 || r <= 0 || s <= 0 || stride <= 0 || pad < 0 || out_h <= 0 || out_w <= 0) return RT_ERR_ARG;
+    if (kp % 8 != 0 || kp < c * r * s) return RT_ERR_ARG;
+    const int64_t total = static_cast<int64_t>(n) * out_h * out_w * (kp / 8);
+    if (total == 0) return RT_OK;
+    im2col_split16_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(static_cast<const float*>(x), static_cast<__half*>(y), c, h, w, r, s, stride,
+                                                                         pad, out_h, out_w, kp, total);
+    note_launch("im2col_split16");
     RT_CHECK_LAUNCH();
     return RT_OK;
 }

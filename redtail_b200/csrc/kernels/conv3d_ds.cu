@@ -274,7 +274,7 @@ float h2f(uint16_t b) {
 }  // namespace
 
 bool ds_shape_supported(const rt_conv3d_desc& d) {
-    if (d.transposed || d.precision != RT_PREC_FP32) return false;
+    if (d.transposed || d.precision != RT_PREC_FP32 || d.act_params) return false;
     if (d.v != 3 || d.r != 3 || d.s != 3) return false;
     for (int i = 0; i < 3; ++i)
         if (d.stride[i] != 1 || d.pad[i] != 1) return false;

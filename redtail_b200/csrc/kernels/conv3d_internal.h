@@ -29,6 +29,7 @@ struct rt_conv3d_plan {
     int out_c_total = 0;        // channels of the output tensor this plan writes into (0: its own cout)
     int out_c_offset = 0;       // first channel this plan writes
     bool reuse_pack = false;    // the packed activations are already in the workspace (written by an earlier part)
+    std::vector<float> act_host;   // [4][cout] s1, b1, s2, b2 of a fused S-ReLU (empty: none); uploaded by tc_plan_init
 };
 
 namespace rt {

@@ -257,6 +257,13 @@ int rt_conv3d_create(const rt_conv3d_desc* d, rt_conv3d_plan** out) {
             pd.out_dims[0] = pd.k;
             pd.weights = static_cast<const char*>(d->weights) + static_cast<size_t>(k0) * per_k * es;
             pd.bias = d->bias ? static_cast<const char*>(d->bias) + static_cast<size_t>(k0) * es : nullptr;
+            std::vector<float> act_part;
+            if (d->act_params) {                 // this part's slice of the [4][K] activation parameters
+                act_part.resize(static_cast<size_t>(4) * pd.k);
+                for (int j = 0; j < 4; ++j)
+                    for (int k = 0; k < pd.k; ++k) act_part[static_cast<size_t>(j) * pd.k + k] = d->act_params[static_cast<size_t>(j) * d->k + k0 + k];
+                pd.act_params = act_part.data();
+            }
             rt_conv3d_plan* part = nullptr;
             const int rc = conv3d_create_part(&pd, d->k, k0, k0 > 0, &part);
             if (rc != RT_OK) { rt_conv3d_destroy(top); return rc; }
@@ -296,6 +303,11 @@ static int conv3d_create_part(const rt_conv3d_desc* d, int out_c_total, int out_
     p->desc.weights = nullptr;
     p->desc.bias = nullptr;
     p->out_c_total = out_c_total; p->out_c_offset = out_c_offset; p->reuse_pack = reuse_pack;
+    if (d->act_params) {
+        if (d->transposed || d->precision == RT_PREC_SIMT || d->fuse_softargmax) { delete p; return RT_ERR_UNSUPPORTED; }
+        p->act_host.assign(d->act_params, d->act_params + static_cast<size_t>(4) * d->k);
+    }
+    p->desc.act_params = nullptr;
     p->out_planes = d->transposed ? d->out_dims[0] - d->slice_d : d->out_dims[1];
     p->cout = d->transposed ? d->c : d->k;
     p->cin = d->transposed ? d->k : d->c;

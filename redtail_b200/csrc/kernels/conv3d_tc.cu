@@ -106,6 +106,7 @@ struct TcParams {
     int out_d, out_h, out_w; // output extent actually written
     long long out_sn, out_sc, out_sd;   // element strides of sample, channel, depth in the dense fp32 output
     int fuse_elu;
+    int fuse_act;            // 1: per-channel S-ReLU  y = max(v*s1 + b1, 0)*s2 + b2  after bias / skip (parameters in shared memory)
     int out_split;           // 1: y (and skip) are RT_LAYOUT_SPLIT16, 0: dense fp32
     int dbg;                 // timing experiments only (REDTAIL_TC_DEBUG bit mask; results are garbage): 1 = epilogue skips the
                              // tcgen05.ld drains, 2 = no MMAs are issued, 4 = the producer moves no data, 8 = no output phase (bias/ELU/stores);
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(kThreadsOf(EW, MT), 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w, const __grid_constant__ TcParams p,
                    const float* __restrict__ bias, const ColInfo* __restrict__ cols, const float* __restrict__ skip,
-                   float* __restrict__ out) {
+                   float* __restrict__ out, const float* __restrict__ act) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // Carve: [stages x stage_bytes] operand ring (1024-aligned) | barriers | tmem address | bias
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -242,6 +243,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     uint32_t* tmem_addr_slot = reinterpret_cast<uint32_t*>(tmem_empty + 8);
     float* s_bias = reinterpret_cast<float*>(tmem_addr_slot + 4);
     ColInfo* s_col = reinterpret_cast<ColInfo*>(s_bias + 128);
+    float* s_act = reinterpret_cast<float*>(s_col + 128);     // [4][128]: s1, b1, s2, b2 (fuse_act)
 
     constexpr int kCoutPad = (EW / 4) * CPH;
     constexpr int kThreads = kThreadsOf(EW, MT);
@@ -267,6 +269,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         s_bias[i] = i < p.cout ? bias[i] : 0.f;
         s_col[i] = cols[i];
     }
+    if (p.fuse_act)
+        for (int i = threadIdx.x; i < 4 * 128; i += kThreads) s_act[i] = ((i & 127) < p.cout) ? act[(i >> 7) * p.cout + (i & 127)] : ((i >> 7) & 1 ? 0.f : 1.f);
     if (warp == 1) tmem_alloc<512>(tmem_addr_slot);      // one CTA per SM: take the whole TMEM (2 accumulator buffers)
     tc_fence_before();
     __syncthreads();
@@ -629,6 +633,13 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[j] += fmaf(__half2float(ll[j]), 1.f / 2048.f, __half2float(hh[j]));
                             }
+                            if (p.fuse_act) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const int ch = c0.ch + j;
+                                    v[j] = fmaf(fmaxf(fmaf(v[j], s_act[ch], s_act[128 + ch]), 0.f), s_act[256 + ch], s_act[384 + ch]);
+                                }
+                            }
                             if (p.fuse_elu) {
 #pragma unroll
                                 for (int j = 0; j < 8; j += 2) elu1_x2(v[j], v[j + 1]);
@@ -658,6 +669,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     for (int j = 0; j < 8; ++j) {
                         if (idx[j] >= 0) {
                             float val = acc0[mt][k0 + j] + s_bias[ch[j]] + sk[j];
+                            if (p.fuse_act) val = fmaf(fmaxf(fmaf(val, s_act[ch[j]], s_act[128 + ch[j]]), 0.f), s_act[256 + ch[j]], s_act[384 + ch[j]]);
                             if (p.fuse_elu) val = elu1(val);
                             out[idx[j]] = val;
                         }
@@ -687,6 +699,7 @@ struct TcPlan {
     int smem_bytes = 0;
     bool in_split = false;            // x arrives as RT_LAYOUT_SPLIT16 (no pack pass)
     ColInfo* d_cols = nullptr;        // device copy of the column table
+    float* act_dev = nullptr;         // [4][cout] S-ReLU parameters (fuse_act)
 };
 
 uint16_t f2h_bits(float f) {
@@ -785,6 +798,7 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     p.ncb = cin / p.kc;
     p.cout = cout; p.cout_pad = cout_pad; p.nb = nb;
     p.fuse_elu = d.fuse_elu;
+    p.fuse_act = plan->act_host.empty() ? 0 : 1;
     const int kdim[3] = {d.v, d.r, d.s};
     int out_ext[3];
     if (!tr) {
@@ -1020,6 +1034,14 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
             return static_cast<int>(cudaErrorMemoryAllocation);
         }
     }
+    if (p.fuse_act) {
+        if (cudaMalloc(&t->act_dev, plan->act_host.size() * sizeof(float)) != cudaSuccess ||
+            cudaMemcpy(t->act_dev, plan->act_host.data(), plan->act_host.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(t->act_dev); cudaFree(t->d_cols);
+            delete t;
+            return static_cast<int>(cudaErrorMemoryAllocation);
+        }
+    }
     t->in_split = d.in_layout == RT_LAYOUT_SPLIT16;
     if (cudaMalloc(&t->w_dev, pk.size() * 2) != cudaSuccess ||
         cudaMemcpy(t->w_dev, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -1059,7 +1081,7 @@ int tc_plan_init(rt_conv3d_plan* plan, const std::vector<float>& w, const std::v
     p.stages = (196 * 1024) / p.stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) { cudaFree(t->w_dev); delete t; return RT_ERR_UNSUPPORTED; }
-    t->smem_bytes = p.stages * p.stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/ + 512 /*bias*/ + 128 * 16 /*column table*/;
+    t->smem_bytes = p.stages * p.stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/ + 512 /*bias*/ + 128 * 16 /*column table*/ + 4 * 128 * 4 /*S-ReLU parameters*/;
     if (t->smem_bytes < 120 * 1024) t->smem_bytes = 120 * 1024;   // > half of the SM: one CTA per SM, so the 512-column TMEM grab never contends
     plan->tc = t;
     return RT_OK;
@@ -1070,6 +1092,7 @@ void tc_plan_destroy(rt_conv3d_plan* plan) {
     if (!t) return;
     cudaFree(t->w_dev);
     cudaFree(t->d_cols);
+    cudaFree(t->act_dev);
     delete t;
     plan->tc = nullptr;
 }
@@ -1144,7 +1167,7 @@ int tc_conv3d_enqueue(const rt_conv3d_plan* plan, int n, const float* x, const f
             RT_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<CPH, SPL, MTT, EWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
             if (dev_ >= 0 && dev_ < 64) attr_set[dev_] = true;                                                        \
         }                                                                                                             \
-        conv3d_umma_kernel<CPH, SPL, MTT, EWW><<<grid, kThreadsOf(EWW, MTT), t->smem_bytes, s>>>(ma_hi, ma_lo, t->map_w, p, plan->bias, t->d_cols, skip, y); \
+        conv3d_umma_kernel<CPH, SPL, MTT, EWW><<<grid, kThreadsOf(EWW, MTT), t->smem_bytes, s>>>(ma_hi, ma_lo, t->map_w, p, plan->bias, t->d_cols, skip, y, t->act_dev); \
     } while (0)
     // 16 epilogue warps (4 column groups) from 32 accumulator columns up; REDTAIL_TC_EW=8 keeps 8.
     static const bool ew8 = getenv("REDTAIL_TC_EW") && atoi(getenv("REDTAIL_TC_EW")) == 8;

@@ -187,7 +187,7 @@ class Conv3d:
 
     def __init__(self, weights, bias, stride, pad_start, in_dims, out_dims=None, transposed=False,
                  precision=PREC_FP32, fuse_elu=False, out_transposed=False, slice_d=0,
-                 in_layout=LAYOUT_DENSE, out_layout=LAYOUT_DENSE, pad_end_d=0, fuse_softargmax=0):
+                 in_layout=LAYOUT_DENSE, out_layout=LAYOUT_DENSE, pad_end_d=0, fuse_softargmax=0, act=None):
         w = np.ascontiguousarray(weights)
         assert w.ndim == 5 and w.dtype in (np.float32, np.float16)
         b = None if bias is None else np.ascontiguousarray(bias).astype(w.dtype)
@@ -213,6 +213,8 @@ class Conv3d:
         d.slice_d = int(slice_d)
         d.in_layout, d.out_layout, d.pad_end_d = int(in_layout), int(out_layout), int(pad_end_d)
         d.fuse_softargmax = int(fuse_softargmax)     # transposed, one output channel: 1 soft-argmin / 2 soft-argmax -> y [N,Hx,Wx]
+        self._act = None if act is None else np.ascontiguousarray(act, dtype=np.float32)    # [4,K]: s1, b1, s2, b2 (fused S-ReLU)
+        d.act_params = self._act.ctypes.data if self._act is not None else None
         self.desc = d
         self.transposed = transposed
         self.out_dims = tuple(out_dims)

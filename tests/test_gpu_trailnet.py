@@ -86,3 +86,50 @@ def test_classifier_layers_vs_oracle():
     sm = torch.empty_like(yo)
     assert lib.rt_softmax_channels(P(yo), P(sm), 7, 3, 1, s) == 0
     np.testing.assert_allclose(sm.cpu().numpy(), torch.softmax(yo.cpu().double(), dim=1).numpy(), rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("cin,cout,stride,h,w_,n", [(64, 64, 1, 43, 78, 2), (128, 256, 1, 22, 39, 3), (256, 256, 2, 22, 39, 2), (64, 128, 2, 11, 20, 1)])
+def test_conv2d_more_than_128_outputs_and_fused_srelu(cin, cout, stride, h, w_, n):
+    """2-D convolutions of the TrailNet blocks on the tcgen05 kernel: more than 128 output channels as <= 128-channel parts, residual add
+    and the S-ReLU chain (Scale -> ReLU -> Scale, per channel) in the epilogue -- against the float64 oracle."""
+    from redtail_b200 import ops as R
+    from oracle import ops as O
+    g = torch.Generator().manual_seed(cin + cout + stride)
+    x = torch.randn(n, 1, cin, h, w_, generator=g)
+    wt = torch.randn(cout, 1, cin, 3, 3, generator=g) * (1.0 / np.sqrt(9 * cin))
+    b = torch.randn(cout, generator=g)
+    act = torch.randn(4, cout, generator=g)
+    ref = O.conv3d(x.double(), wt.double(), b.double(), (1, stride, stride), (0, 1, 1))          # [N, K, 1, Ho, Wo]
+    skip = torch.randn(ref.shape, generator=g).float()
+    v = lambda t: t.double().view(1, -1, 1, 1, 1)
+    ref_act = torch.relu((ref + skip.double()) * v(act[0]) + v(act[1])) * v(act[2]) + v(act[3])
+    op = R.Conv3d(wt.numpy(), b.numpy(), (1, stride, stride), (0, 1, 1), (1, cin, h, w_), precision=R.PREC_FP32, act=act.numpy())
+    y = op(x.cuda(), skip=skip.cuda())
+    assert "umma" in R.last_kernel(), R.last_kernel()
+    np.testing.assert_allclose(y.cpu().numpy(), ref_act.float().numpy(), rtol=0, atol=3e-4)
+    op2 = R.Conv3d(wt.numpy(), b.numpy(), (1, stride, stride), (0, 1, 1), (1, cin, h, w_), precision=R.PREC_FP32)
+    np.testing.assert_allclose(op2(x.cuda()).cpu().numpy(), ref.float().numpy(), rtol=0, atol=3e-4)
+
+
+def test_im2col_conv_7x7():
+    """TrailNet conv1 as im2col + 1x1 tensor-core convolution == the plain 7x7 stride-2 convolution."""
+    import ctypes as C
+    from redtail_b200 import ops as R
+    from redtail_b200._lib import kernels_lib
+    from oracle import ops as O
+    g = torch.Generator().manual_seed(9)
+    n, c, h, w_, k = 2, 3, 45, 80, 64
+    x = torch.rand(n, c, h, w_, generator=g) * 255
+    wt = torch.randn(k, c, 7, 7, generator=g) * 0.01
+    b = torch.randn(k, generator=g)
+    ref = O.conv2d(x.double(), wt.double(), b.double(), (2, 2), (0, 0))
+    ho, wo, kp = ref.shape[2], ref.shape[3], 192
+    m = torch.empty((n, 2, 1, ho, wo, kp), dtype=torch.float16, device="cuda")
+    rc = kernels_lib().rt_im2col_split16(C.c_void_p(x.cuda().data_ptr()), C.c_void_p(m.data_ptr()), n, c, h, w_, 7, 7, 2, 0, ho, wo, kp,
+                                          C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    w2 = torch.zeros(k, 1, kp, 1, 1)
+    w2[:, 0, :147, 0, 0] = wt.reshape(k, 147)
+    op = R.Conv3d(w2.numpy(), b.numpy(), (1, 1, 1), (0, 0, 0), (1, kp, ho, wo), precision=R.PREC_FP32, in_layout=R.LAYOUT_SPLIT16)
+    y = op(m)                                                   # [N, K, 1, Ho, Wo]
+    np.testing.assert_allclose(y.cpu().numpy()[:, :, 0], ref.float().numpy(), rtol=0, atol=2e-3)      # values up to ~30
