@@ -839,7 +839,8 @@ bool EngineImpl::build(NetworkImpl& net, int max_batch, bool half2)
                 const int gemm_k = cd.cin * cd.r * cd.s;
                 const char* s16_env = getenv("REDTAIL_ENGINE_SPLIT16");
                 const char* i2c_env = getenv("REDTAIL_ENGINE_IM2COL");
-                if (!tc2 && !tr2 && fusion && !simt_only && (cd.r > 3 || cd.s > 3) && gemm_k > 96 && gemm_k <= 512 &&
+                const int min_k = getenv("REDTAIL_ENGINE_IM2COL_MINK") ? atoi(getenv("REDTAIL_ENGINE_IM2COL_MINK")) : 96;
+                if (!tc2 && !tr2 && fusion && !simt_only && (cd.r > 3 || cd.s > 3) && gemm_k > min_k && gemm_k <= 512 &&
                     !(s16_env && s16_env[0] == '0') && !(i2c_env && i2c_env[0] == '0') && cd.stride[0] == cd.stride[1] && cd.pad[0] == cd.pad[1]) {
                     const int kp = (gemm_k + 63) / 64 * 64;
                     // weights [cout][cin*r*s] -> [cout][kp], zero padded, fp32 (the engine owns the buffer)

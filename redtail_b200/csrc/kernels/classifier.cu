@@ -94,32 +94,41 @@ softmax_channels_kernel(const float* __restrict__ x, float* __restrict__ y, int 
 // im2col for 2-D convolutions with filters larger than 3x3 (TrailNet conv1: 7x7, stride 2, 3 channels): x [n,c,h,w] fp32 ->
 // RT_LAYOUT_SPLIT16 matrix [n][hi|lo][1][ho][wo][kp] with K index = (ci * r + ri) * s + si (the KCRS order of the weights), zero
 // beyond c*r*s.  The convolution itself is then a 1x1 convolution over kp "channels" on the tcgen05 kernel.
-// One thread = one output position x 8 consecutive K (one 16-byte vector per fp16 plane); K groups fastest -> coalesced stores.
+// One CTA = one output row of one sample: the c*r input rows it reads are staged in shared memory once (each input element is
+// used by up to r*s/stride^2 outputs), a table maps K -> (offset in the tile, filter column); one thread-item = one output
+// position x 8 consecutive K = one 16-byte vector per fp16 plane, K groups fastest so that the stores of a warp are contiguous.
 __global__ void __launch_bounds__(256)
 im2col_split16_kernel(const float* __restrict__ x, __half* __restrict__ y, int c, int h, int w, int r, int s, int stride, int pad,
-                      int ho, int wo, int kp, int64_t total) {
-    const int groups = kp >> 3, krs = c * r * s;
+                      int ho, int wo, int kp) {
+    extern __shared__ float im_tile[];                     // [c*r][w] input rows, then int2 table[kp]
+    int2* tab = reinterpret_cast<int2*>(im_tile + ((static_cast<size_t>(c) * r * w + 1) & ~static_cast<size_t>(1)));      // 8-byte aligned
+    const int oy = blockIdx.x, n = blockIdx.y;
+    const int krs = c * r * s, groups = kp >> 3;
+    const float* xn = x + static_cast<int64_t>(n) * c * h * w;
+    for (int i = threadIdx.x; i < c * r * w; i += blockDim.x) {
+        const int ix = i % w, row = i / w, ri = row % r, ci = row / r;
+        const int iy = oy * stride - pad + ri;
+        im_tile[i] = (iy >= 0 && iy < h) ? __ldg(xn + (static_cast<int64_t>(ci) * h + iy) * w + ix) : 0.f;
+    }
+    for (int k = threadIdx.x; k < kp; k += blockDim.x) {
+        const int si = k % s, row = k / s;                 // row = ci * r + ri
+        tab[k] = k < krs ? make_int2(row * w, si) : make_int2(-1, 0);
+    }
+    __syncthreads();
     const int64_t plane = static_cast<int64_t>(ho) * wo * kp;          // halves of one fp16 plane per sample
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(i % groups);
-        const int64_t pos = i / groups;
-        const int ox = static_cast<int>(pos % wo), oy = static_cast<int>((pos / wo) % ho);
-        const int64_t n = pos / (static_cast<int64_t>(wo) * ho);
-        const float* xn = x + n * c * h * w;
+    __half* yn = y + static_cast<int64_t>(n) * 2 * plane + static_cast<int64_t>(oy) * wo * kp;
+    for (int i = threadIdx.x; i < wo * groups; i += blockDim.x) {
+        const int g = i % groups, ox = i / groups;
+        const int x0 = ox * stride - pad;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int k = g * 8 + j;
-            float val = 0.f;
-            if (k < krs) {
-                const int si = k % s, ri = (k / s) % r, ci = k / (r * s);
-                const int iy = oy * stride - pad + ri, ix = ox * stride - pad + si;
-                if (iy >= 0 && iy < h && ix >= 0 && ix < w) val = __ldg(xn + (static_cast<int64_t>(ci) * h + iy) * w + ix);
-            }
-            v[j] = val;
+            const int2 t = tab[g * 8 + j];
+            const int ix = x0 + t.y;
+            v[j] = (t.x >= 0 && ix >= 0 && ix < w) ? im_tile[t.x + ix] : 0.f;
         }
-        const int64_t o = n * 2 * plane + (static_cast<int64_t>(oy) * wo + ox) * kp + g * 8;
-        split_store8(v, y + o, y + plane + o);
+        const int64_t o = static_cast<int64_t>(ox) * kp + g * 8;
+        split_store8(v, yn + o, yn + plane + o);
     }
 }
 
@@ -202,11 +211,13 @@ extern "C" int rt_softmax_channels(const void* x, void* y, int n, int c, int64_t
 extern "C" int rt_im2col_split16(const void* x, void* y, int n, int c, int h, int w, int r, int s, int stride, int pad, int out_h, int out_w,
                                  int kp, void* stream) {
     if (!x || !y || n < 0 || c <= 0 || h <= 0 || w <= 0 || r <= 0 || s <= 0 || stride <= 0 || pad < 0 || out_h <= 0 || out_w <= 0) return RT_ERR_ARG;
-    if (kp % 8 != 0 || kp < c * r * s) return RT_ERR_ARG;
-    const int64_t total = static_cast<int64_t>(n) * out_h * out_w * (kp / 8);
-    if (total == 0) return RT_OK;
-    im2col_split16_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(static_cast<const float*>(x), static_cast<__half*>(y), c, h, w, r, s, stride,
-                                                                         pad, out_h, out_w, kp, total);
+    if (kp % 8 != 0 || kp < c * r * s || n > 65535) return RT_ERR_ARG;
+    if (n == 0) return RT_OK;
+    const size_t smem = ((static_cast<size_t>(c) * r * w + 1) & ~static_cast<size_t>(1)) * sizeof(float) + static_cast<size_t>(kp) * sizeof(int2);
+    if (smem > 200 * 1024) return RT_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024) RT_CUDA(cudaFuncSetAttribute(im2col_split16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    im2col_split16_kernel<<<dim3(out_h, n), 256, smem, as_stream(stream)>>>(static_cast<const float*>(x), static_cast<__half*>(y), c, h, w, r, s, stride,
+                                                                           pad, out_h, out_w, kp);
     note_launch("im2col_split16");
     RT_CHECK_LAUNCH();
     return RT_OK;
