@@ -32,10 +32,12 @@
 // the epilogue warps add every chunk into fp32 registers with round-to-nearest while the next chunk runs in another TMEM
 // buffer.  What a chunk boundary costs and what it does not (TMEM reads are free) is measured in profiles/r01_ncu_full_kernels.md.
 //
-// CTA = 10 warps: warp 0 TMA producer, warp 1 MMA issuer (elect.sync; + TMEM allocation, all 512 columns = 2..8
-// accumulator buffers), warps 2-9 epilogue (tcgen05.ld -> registers -> bias / skip / ELU -> dense fp32 or split16 stores;
-// each warp owns one TMEM lane quarter and one half of the columns).  Persistent grid (one CTA per SM), static round-robin
-// tile schedule, 2..8-stage smem operand ring.
+// CTA = 11 or 19 warps: warp 0 TMA producer, warps 1-2 MMA issuers on alternate accumulation chunks (elect.sync; warp 1 also owns
+// the TMEM allocation, all 512 columns = 2..8 accumulator buffers), 8 or 16 epilogue warps (tcgen05.ld -> registers -> bias / skip /
+// S-ReLU / ELU -> dense fp32 or split16 stores; each warp owns one TMEM lane quarter and one of 2 / 4 column groups).  Persistent
+// grid (one CTA per SM), static round-robin tile schedule, 2..8-stage smem operand ring.  Forward convolutions with more than 128
+// output channels run as <= 128-channel parts (rt_conv3d_create); 32 -> 32 layers and the final 32 -> 1 transposed conv have their own
+// depth-stationary kernels (conv3d_ds.cu, deconv_softargmax.cu).
 #include <cstdlib>
 #include <cstring>
 #include <vector>
