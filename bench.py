@@ -29,6 +29,29 @@ WEIGHTS = os.path.join(ROOT, "tests", "golden", "weights", "nvsmall_fp32.bin")
 PUBLISHED_PAIRS_PER_S = 1000.0 / 450.0
 
 
+_JSON_FD = None
+
+
+def stdout_for_json_only(world):
+    """Under torchrun NCCL prints its banner / INFO log with printf to fd 1; the contract wants exactly ONE JSON line on stdout.
+    For world > 1 fd 1 is pointed at stderr for the life of the process (so the NCCL_DEBUG=INFO log -- communicator size, rings /
+    NVLS, transports -- is still recorded, on stderr) and the JSON line is written to the saved descriptor by emit()."""
+    global _JSON_FD
+    if world > 1 and _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = json.dumps(obj) + "\n"
+    if _JSON_FD is None:
+        sys.stdout.write(line)
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line.encode())
+
+
 def synthetic_pairs(batch, seed=1234):
     """KITTI-shaped synthetic stereo pairs, float32 [B,3,H,W] in [0,1]: smooth random texture + noise; the right image
     is the left one warped by a piecewise-planar disparity in [2, 80] px so the cost volume has real structure."""
@@ -231,9 +254,9 @@ def run_other_config(args):
         raise SystemExit("bench.py: no CUDA device -- this engine has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
+        stdout_for_json_only(world)
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH,ENV")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from redtail_b200 import StereoEngine, ops
     from redtail_b200.parallel import OverlappedGather
@@ -323,7 +346,7 @@ def run_other_config(args):
     tf = cfg["gflop_per_pair"] * B / stack_ms if stack_ms > 0 else 0.0          # GFLOP / ms = TFLOP/s
     pairs = world * B * args.steps
     value = pairs / (ms * 1e-3)
-    print(json.dumps({
+    emit(({
         "metric": "stereo pairs/sec %s" % cfg["what"], "value": value, "unit": "stereo pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 activations (fp16-split tensor-core products), fp16 weights", "data": "synthetic",
@@ -356,9 +379,9 @@ def run_trailnet(args):
         raise SystemExit("bench.py: no CUDA device -- this engine has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
+        stdout_for_json_only(world)
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH,ENV")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from redtail_b200 import CaffeNet, ops
     tn = os.path.join(ROOT, "tests", "golden", "trailnet")
@@ -425,7 +448,7 @@ def run_trailnet(args):
     gflop_img = 5.20                                         # TrailNet 5.20 GFLOP / image
     tf = gflop_img * B / conv_ms if conv_ms > 0 else 0.0     # GFLOP / ms = TFLOP/s
     imgs = world * B * args.steps
-    print(json.dumps({
+    emit(({
         "metric": "images/sec TrailNet S-ResNet-18 320x180", "value": imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (fp16-split tensor-core products)", "data": "synthetic",
@@ -477,11 +500,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- this engine has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL writes its debug log to STDOUT unless told otherwise, and stdout must carry exactly one JSON line: send the
-        # INFO log (communicator size, rings/NVLS, transports) to stderr instead of silencing it.
+        # NCCL writes its banner and debug log to STDOUT, and stdout must carry exactly one JSON line: fd 1 is pointed at stderr
+        # (the INFO log -- communicator size, rings/NVLS, transports -- stays available there) and the JSON goes to the saved fd.
+        stdout_for_json_only(world)
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH,ENV")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from redtail_b200 import StereoEngine, ops
@@ -705,7 +728,7 @@ def main():
         out["literal_layers"] = literal
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 

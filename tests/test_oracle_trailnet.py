@@ -76,3 +76,31 @@ def test_cpp_caffe_parser_plan_matches_oracle(model):
     (y,) = P.execute(pl, {"data": x.astype(np.float64)}).values()
     np.testing.assert_allclose(y.reshape(5, 6), exp["oracle_f64"], rtol=0, atol=1e-12)
     assert lib.rt_caffe_dump_plan(b"/nonexistent.prototxt", args[1], b"out", 1, None, 0) == 0          # loud failure, no crash
+
+
+def test_cpp_caffe_parser_rejects_malformed_models(tmp_path):
+    """Truncated / corrupted model files and unsupported layers fail loudly (return value 0 + message), they do not crash."""
+    from redtail_b200._lib import engine_lib
+    lib = engine_lib()
+    proto = open(os.path.join(TN, "TrailNet_SResNet-18.prototxt")).read()
+    model = open(os.path.join(TN, "TrailNet_SResNet-18.caffemodel"), "rb").read()
+    good_p, good_m = os.path.join(TN, "TrailNet_SResNet-18.prototxt").encode(), os.path.join(TN, "TrailNet_SResNet-18.caffemodel").encode()
+
+    def dump(p, m, blob=b"out"):
+        return lib.rt_caffe_dump_plan(p, m, blob, 1, None, 0)
+
+    cases = {"trunc.caffemodel": model[:len(model) // 3], "garbage.caffemodel": bytes(range(256)) * 64, "empty.caffemodel": b""}
+    for name, data in cases.items():
+        f = tmp_path / name
+        f.write_bytes(data)
+        assert dump(good_p, str(f).encode()) == 0, name
+    bad = {"unbalanced.prototxt": proto[:len(proto) // 2],                                   # ends inside a layer { ... }
+           "lrn.prototxt": proto.replace('type: "Softmax"', 'type: "LRN"', 1),                # a layer type the parser does not map
+           "nodim.prototxt": proto.replace("input_shape", "input_shapeX", 1),
+           "badbottom.prototxt": proto.replace('bottom: "pool1"', 'bottom: "no_such_blob"', 1)}
+    for name, text in bad.items():
+        f = tmp_path / name
+        f.write_text(text)
+        assert dump(str(f).encode(), good_m) == 0, name
+    assert dump(good_p, good_m, b"no_such_output") == 0
+    assert dump(good_p, good_m) > 0
