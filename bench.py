@@ -255,7 +255,8 @@ def run_other_config(args):
     torch.cuda.set_device(local)
     if world > 1:
         stdout_for_json_only(world)
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):      # the boxes preset a quieter level: no rank / topology lines
+            os.environ["NCCL_DEBUG"] = "INFO"
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH,ENV")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from redtail_b200 import StereoEngine, ops
@@ -380,7 +381,8 @@ def run_trailnet(args):
     torch.cuda.set_device(local)
     if world > 1:
         stdout_for_json_only(world)
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):      # the boxes preset a quieter level: no rank / topology lines
+            os.environ["NCCL_DEBUG"] = "INFO"
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH,ENV")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from redtail_b200 import CaffeNet, ops
@@ -503,7 +505,8 @@ def main():
         # NCCL writes its banner and debug log to STDOUT, and stdout must carry exactly one JSON line: fd 1 is pointed at stderr
         # (the INFO log -- communicator size, rings/NVLS, transports -- stays available there) and the JSON goes to the saved fd.
         stdout_for_json_only(world)
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):      # the boxes preset a quieter level: no rank / topology lines
+            os.environ["NCCL_DEBUG"] = "INFO"
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH,ENV")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
