@@ -368,7 +368,7 @@ def run_other_config(args):
 def run_trailnet(args):
     """bench.py --config trailnet: BASELINE configs[4], "TrailNet ResNet-18 320x180 batch=256 on 1 B200 (2D-conv tensor-core path,
     orientation+translation heads)".  A step = one batch of synthetic 320x180 BGR frames through the S-ResNet-18 classifier
-    (models/pretrained/TrailNet_SResNet-18.{prototxt,caffemodel}, committed under tests/golden/trailnet/) loaded by the
+    (the reference's models/pretrained/TrailNet_SResNet-18.{prototxt,caffemodel}, fixtures under tests/golden/trailnet/) loaded by the
     nvcaffeparser1-compatible parser; unit = images/s.  Parity: the reference's five test images against the predictions its own
     test expects (ros/packages/caffe_ros/tests/tests.cpp:64-69, 1e-3)."""
     import torch
@@ -388,7 +388,12 @@ def run_trailnet(args):
     from redtail_b200 import CaffeNet, ops
     tn = os.path.join(ROOT, "tests", "golden", "trailnet")
     B = args.batch if args.batch_given else 256
-    net = CaffeNet(os.path.join(tn, "TrailNet_SResNet-18.prototxt"), os.path.join(tn, "TrailNet_SResNet-18.caffemodel"), "out", max_batch=B)
+    import gzip
+    import tempfile
+    proto = os.path.join(tempfile.gettempdir(), "redtail_b200_bench_sresnet18_%d_%d.prototxt" % (os.getuid(), rank))      # the parser takes file paths
+    with open(proto, "wb") as f:
+        f.write(gzip.open(os.path.join(tn, "sresnet18_deploy.prototxt.gz"), "rb").read())
+    net = CaffeNet(proto, os.path.join(tn, "sresnet18_weights.caffemodel"), "out", max_batch=B)
     rng = np.random.default_rng(1234 + rank)
     h_in = torch.from_numpy(rng.uniform(0, 255, (B, 3, 180, 320)).astype(np.float32)).pin_memory()
     h_out = torch.empty((B, 6, 1, 1), dtype=torch.float32).pin_memory()

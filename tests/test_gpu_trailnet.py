@@ -9,9 +9,10 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+from tests.util import trailnet_model_files
+
 TN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trailnet")
-PROTO = os.path.join(TN, "TrailNet_SResNet-18.prototxt")
-MODEL = os.path.join(TN, "TrailNet_SResNet-18.caffemodel")
+PROTO, MODEL = trailnet_model_files()
 
 
 @pytest.fixture(scope="module")

@@ -6,14 +6,15 @@ import numpy as np
 import pytest
 
 from oracle import caffe
+from tests.util import trailnet_model_files
 
 TN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trailnet")
+PROTO, MODEL = trailnet_model_files()
 
 
 @pytest.fixture(scope="module")
 def model():
-    return (open(os.path.join(TN, "TrailNet_SResNet-18.prototxt")).read(),
-            caffe.read_caffemodel(os.path.join(TN, "TrailNet_SResNet-18.caffemodel")))
+    return open(PROTO).read(), caffe.read_caffemodel(MODEL)
 
 
 def test_caffemodel_reader_shapes(model):
@@ -60,7 +61,7 @@ def test_cpp_caffe_parser_plan_matches_oracle(model):
     from redtail_b200._lib import engine_lib
     from oracle import plan as P
     lib = engine_lib()
-    args = (os.path.join(TN, "TrailNet_SResNet-18.prototxt").encode(), os.path.join(TN, "TrailNet_SResNet-18.caffemodel").encode(), b"out", 1)
+    args = (PROTO.encode(), MODEL.encode(), b"out", 1)
     n = lib.rt_caffe_dump_plan(*args, None, 0)
     assert n > 40e6, lib.rt_stereo_last_error()
     buf = C.create_string_buffer(n)
@@ -82,9 +83,9 @@ def test_cpp_caffe_parser_rejects_malformed_models(tmp_path):
     """Truncated / corrupted model files and unsupported layers fail loudly (return value 0 + message), they do not crash."""
     from redtail_b200._lib import engine_lib
     lib = engine_lib()
-    proto = open(os.path.join(TN, "TrailNet_SResNet-18.prototxt")).read()
-    model = open(os.path.join(TN, "TrailNet_SResNet-18.caffemodel"), "rb").read()
-    good_p, good_m = os.path.join(TN, "TrailNet_SResNet-18.prototxt").encode(), os.path.join(TN, "TrailNet_SResNet-18.caffemodel").encode()
+    proto = open(PROTO).read()
+    model = open(MODEL, "rb").read()
+    good_p, good_m = PROTO.encode(), MODEL.encode()
 
     def dump(p, m, blob=b"out"):
         return lib.rt_caffe_dump_plan(p, m, blob, 1, None, 0)

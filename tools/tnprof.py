@@ -2,9 +2,10 @@
 import sys, numpy as np, torch, time
 sys.path.insert(0, ".")
 from redtail_b200 import CaffeNet
-TN = "tests/golden/trailnet/"
+from tests.util import trailnet_model_files
+PROTO, MODEL = trailnet_model_files()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-net = CaffeNet(TN + "TrailNet_SResNet-18.prototxt", TN + "TrailNet_SResNet-18.caffemodel", "out", max_batch=B)
+net = CaffeNet(PROTO, MODEL, "out", max_batch=B)
 x = torch.rand(B, 3, 180, 320).cuda() * 255
 rows = net.profile(x)
 for n, ms in rows: print("  %-60s %.3f" % (n[:60], ms))
