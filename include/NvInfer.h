@@ -403,6 +403,25 @@ protected:
     virtual ~ICudaEngine() {}
 };
 
+// INT8 calibration interfaces: declared so that ros/packages/caffe_ros (int8_calibrator.h, tensor_net.cpp:293-301) compiles
+// unchanged.  This engine has no INT8 path: platformHasFastInt8() is false, so the reference never switches it on; a builder that
+// is put into INT8 mode anyway refuses to build (loudly).
+enum class CalibrationAlgoType : int { kLEGACY_CALIBRATION = 0, kENTROPY_CALIBRATION = 1 };
+class IInt8Calibrator {
+public:
+    virtual int getBatchSize() const = 0;
+    virtual bool getBatch(void* bindings[], const char* names[], int nbBindings) = 0;
+    virtual const void* readCalibrationCache(std::size_t& length) = 0;
+    virtual void writeCalibrationCache(const void* ptr, std::size_t length) = 0;
+    virtual CalibrationAlgoType getAlgorithm() = 0;
+    virtual ~IInt8Calibrator() {}
+};
+class IInt8EntropyCalibrator : public IInt8Calibrator {
+public:
+    CalibrationAlgoType getAlgorithm() override { return CalibrationAlgoType::kENTROPY_CALIBRATION; }
+    virtual ~IInt8EntropyCalibrator() {}
+};
+
 class IBuilder {
 public:
     virtual INetworkDefinition* createNetwork() = 0;
@@ -422,6 +441,9 @@ public:
     virtual bool platformHasFastFp16() const = 0;
     virtual bool platformHasFastInt8() const = 0;
     virtual void destroy() = 0;
+    virtual void setInt8Mode(bool mode) = 0;
+    virtual bool getInt8Mode() const = 0;
+    virtual void setInt8Calibrator(IInt8Calibrator* calibrator) = 0;
 protected:
     virtual ~IBuilder() {}
 };

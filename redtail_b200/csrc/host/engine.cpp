@@ -74,7 +74,16 @@ struct PlanReader {
         pos += n;
         return v;
     }
-    Dims dims() { Dims d{}; d.nbDims = get<int32_t>(); for (int i = 0; i < Dims::MAX_DIMS; ++i) d.d[i] = get<int32_t>(); return d; }
+    Dims dims()
+    {
+        Dims d{};
+        d.nbDims = get<int32_t>();
+        for (int i = 0; i < Dims::MAX_DIMS; ++i) d.d[i] = get<int32_t>();
+        // The plan does not store the dimension types; a 3-D tensor of these networks is CHW (DimsCHW), which callers of
+        // getBindingDimensions() on a deserialised engine check (ros/packages/caffe_ros/src/tensor_net.cpp:21-28).
+        if (d.nbDims == 3) d.type[0] = DimensionType::kCHANNEL;
+        return d;
+    }
     void align8() { pos = (pos + 7) & ~static_cast<size_t>(7); }
     Weights weights()          // values point into the plan copy the engine keeps alive
     {
@@ -1804,6 +1813,10 @@ public:
             logMsg(log_, ILogger::Severity::kERROR, "buildCudaEngine: no CUDA device (this engine has no CPU path).");
             return nullptr;
         }
+        if (int8_) {
+            logMsg(log_, ILogger::Severity::kERROR, "buildCudaEngine: INT8 mode is not supported (platformHasFastInt8() is false); use fp32 or fp16.");
+            return nullptr;
+        }
         auto* e = new EngineImpl(log_);
         if (!e->build(static_cast<NetworkImpl&>(network), max_batch_, half2_)) {
             delete e;
@@ -1814,12 +1827,15 @@ public:
     bool platformHasFastFp16() const override { return true; }
     bool platformHasFastInt8() const override { return false; }
     void destroy() override { delete this; }
+    void setInt8Mode(bool m) override { int8_ = m; }
+    bool getInt8Mode() const override { return int8_; }
+    void setInt8Calibrator(IInt8Calibrator*) override {}
 
 private:
     ILogger& log_;
     int max_batch_ = 1, min_find_ = 1, avg_find_ = 1;
     size_t max_ws_ = 0;
-    bool half2_ = false, debug_sync_ = false;
+    bool half2_ = false, debug_sync_ = false, int8_ = false;
 };
 
 class RuntimeImpl : public IRuntime {

@@ -4,6 +4,7 @@
   tests/golden/trailnet/inputs.npz      the five test images of ros/packages/caffe_ros/tests/data as the network sees them:
                                         cv::imread -> float -> cv::resize(320x180, INTER_CUBIC) -> CHW, BGR, 0..255
                                         (ros/packages/caffe_ros/src/tensor_net.cpp:303-336 with the test node's defaults)
+  tests/golden/trailnet/frames_rgb8.npz two of the images as 8-bit RGB camera frames [2,504,640,3] (what tests.cpp publishes)
   tests/golden/trailnet/expected.npz    `tests_cpp`: the predictions ros/packages/caffe_ros/tests/tests.cpp:64-69 expects (1e-3);
                                         `oracle_f64`: oracle/caffe.py in float64 on the same inputs
 """
@@ -35,6 +36,10 @@ tests_cpp = np.array([[0.932, 0.060, 0.006, 0.080, 0.848, 0.071],
                       [0.000, 0.855, 0.144, 0.013, 0.031, 0.954]], np.float64)
 x = np.stack([caffe.preprocess_bgr8(cv2.imread(os.path.join(REF, "ros/packages/caffe_ros/tests/data", n)), 320, 180) for n in names])
 np.savez_compressed(os.path.join(OUT, "inputs.npz"), images=x.astype(np.float32), names=np.array(names))
+# two camera frames as the test publishes them (tests.cpp:28-48: cv::imread, BGR -> RGB, encoding rgb8), for the drop-in run of the
+# reference's unchanged tensor_net.cpp (tools/dropin/trailnet_driver.cpp): rows 0 and 4 of the tables above
+frames = np.stack([cv2.cvtColor(cv2.imread(os.path.join(REF, "ros/packages/caffe_ros/tests/data", n)), cv2.COLOR_BGR2RGB) for n in (names[0], names[4])])
+np.savez_compressed(os.path.join(OUT, "frames_rgb8.npz"), frames=frames, rows=np.array([0, 4]))
 blobs = caffe.read_caffemodel(os.path.join(OUT, "sresnet18_weights.caffemodel"))
 proto = proto_bytes.decode()
 y = caffe.run_net(proto, blobs, x.astype(np.float64))

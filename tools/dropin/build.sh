@@ -1,6 +1,6 @@
 #!/bin/bash
-# Drop-in proof: compiles the UNCHANGED reference sources -- the gtest suite stereoDNN/tests/tests_main.cpp and the four
-# generated network builders stereoDNN/sample_app/*_net.cpp -- where they lie under /root/reference, against this repo's
+# Drop-in proof: compiles the UNCHANGED reference sources -- the gtest suite stereoDNN/tests/tests_main.cpp, the four
+# generated network builders stereoDNN/sample_app/*_net.cpp, sample_app/main.cpp and the TrailNet runtime of ros/packages/caffe_ros -- where they lie under /root/reference, against this repo's
 # headers (include/NvInfer.h, redtail_tensorrt_plugins.h, internal_utils.h) and links them to libnvstereo_inference.so.
 # Outputs go to dropin/_ref/ (git-ignored, travels to the GPU box like the other built binaries).  Only runs where
 # /root/reference exists; nothing is copied from it.
@@ -40,4 +40,15 @@ ls -la "$OUT/plans"
 # against the cv:: stand-in of tools/dropin/include/opencv2 (OpenCV's C++ headers are not in this image).
 $CXX $INC -I"$REF/sample_app" -c "$REF/sample_app/main.cpp" -o "$OUT/main.o"
 $CXX -o "$OUT/nvstereo_sample_app" "$OUT/main.o" "$OUT"/*_net.o $LIB -lz
-echo "built: $OUT/nvstereo_tests $OUT/nvstereo_net_driver $OUT/nvstereo_sample_app"
+# The reference's TrailNet runtime, UNCHANGED (ros/packages/caffe_ros/src/tensor_net.cpp + int8_calibrator.cpp: Caffe parser ->
+# buildCudaEngine -> serialize -> deserializeCudaEngine -> execute), against NvInfer.h / NvCaffeParser.h and the ros / boost / cv
+# stand-ins of tools/dropin/include (neither ROS nor Boost nor OpenCV's C++ headers are in this image); driven like caffe_ros.cpp does.
+CR=/root/reference/ros/packages/caffe_ros
+if [ -d "$CR" ]; then
+  CXX17="${CXX:-g++} -std=c++17 -O1 -w"
+  $CXX17 $INC -I"$CR/include" -c "$CR/src/tensor_net.cpp" -o "$OUT/tensor_net.o"
+  $CXX17 $INC -I"$CR/include" -c "$CR/src/int8_calibrator.cpp" -o "$OUT/int8_calibrator.o"
+  $CXX17 $INC -I"$CR/include" -c "$ROOT/tools/dropin/trailnet_driver.cpp" -o "$OUT/trailnet_driver.o"
+  $CXX17 -o "$OUT/caffe_ros_trailnet" "$OUT/trailnet_driver.o" "$OUT/tensor_net.o" "$OUT/int8_calibrator.o" $LIB -lz
+fi
+echo "built: $OUT/nvstereo_tests $OUT/nvstereo_net_driver $OUT/nvstereo_sample_app $OUT/caffe_ros_trailnet"

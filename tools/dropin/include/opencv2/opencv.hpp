@@ -2,7 +2,9 @@
 //   * tests/tests_main.cpp:200-202,237-239 -- cv::Mat over a float vector + cv::convertFp16 (dead code there);
 //   * sample_app/main.cpp:83-98            -- readImgFile: imread, convertTo(CV_32F), resize(INTER_AREA), cvtColor(BGR2RGB),
 //                                             reshape(1, w*h).t(), /= 255.0, ptr<float>();
-//   * sample_app/main.cpp:317-330          -- Mat(h, w, CV_32F, ptr), *= 256, convertTo(CV_16U), imwrite(".png").
+//   * sample_app/main.cpp:317-330          -- Mat(h, w, CV_32F, ptr), *= 256, convertTo(CV_16U), imwrite(".png");
+//   * ros/packages/caffe_ros/src/tensor_net.cpp:262-336 -- Mat over the caller's 8-bit image, cvtColor (RGB/BGRA -> BGR/RGB), convertTo,
+//                                             resize(INTER_CUBIC), *= scale, += shift, reshape(1, w*h).t(), isContinuous, size().area().
 // Test / drop-in infrastructure only (tools/dropin); the product's own image path is rt_preprocess_bgr8 /
 // rt_disparity_to_u16 / rt_write_png16 (include/redtail_b200.h).  Semantics follow OpenCV 4: INTER_AREA uses OpenCV's area
 // tables (same sums, same order -- the restatement is checked against cv2 in tests/test_dropin_shim.py), convertTo
@@ -10,11 +12,13 @@
 #pragma once
 #include <zlib.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>       // OpenCV's core headers bring the standard containers in; caffe_ros/int8_calibrator.h:31 relies on that
 #include <memory>
 #include <sstream>     // OpenCV's core headers bring it in; sample_app/main.cpp:214 relies on that
 #include <string>
@@ -26,19 +30,25 @@
 #define CV_32F 5
 #define CV_MAKETYPE(depth, cn) ((depth) + (((cn) - 1) << 3))
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_8UC4 CV_MAKETYPE(CV_8U, 4)
 #define CV_32FC3 CV_MAKETYPE(CV_32F, 3)
+#define CV_BGRA2BGR 1
+#define CV_BGRA2RGB 3
 #define CV_BGR2RGB 4
+#define CV_RGB2BGR 4
 
 namespace cv {
 
 typedef unsigned char uchar;
 
 enum InterpolationFlags { INTER_NEAREST = 0, INTER_LINEAR = 1, INTER_CUBIC = 2, INTER_AREA = 3 };
-enum ColorConversionCodes { COLOR_BGR2RGB = 4 };
+enum ColorConversionCodes { COLOR_BGRA2BGR = 1, COLOR_BGRA2RGB = 3, COLOR_BGR2RGB = 4, COLOR_RGB2BGR = 4 };
+enum ImreadModes { IMREAD_UNCHANGED = -1, IMREAD_GRAYSCALE = 0, IMREAD_COLOR = 1 };
 
 struct Size {
     Size() {}
     Size(int w, int h) : width(w), height(h) {}
+    int area() const { return width * height; }
     int width = 0, height = 0;
 };
 
@@ -58,6 +68,8 @@ public:
     size_t elemSize1() const { return depth() == CV_8U ? 1 : (depth() == CV_32F ? 4 : 2); }
     size_t total() const { return static_cast<size_t>(rows) * cols; }
     bool empty() const { return data == nullptr || total() == 0; }
+    bool isContinuous() const { return true; }        // this stand-in never creates padded rows
+    Size size() const { return Size(cols, rows); }
     void create(int r, int c, int type)
     {
         rows = r; cols = c; type_ = type;
@@ -123,6 +135,14 @@ public:
         return *this;
     }
     Mat& operator/=(double s) { return *this *= 1.0 / s; }
+    Mat& operator+=(double s)      // OpenCV: add(*this, Scalar(s), *this) -- fp32 add of float(s)
+    {
+        if (depth() != CV_32F) std::abort();
+        float* p = reinterpret_cast<float*>(data);
+        const float f = static_cast<float>(s);
+        for (size_t i = 0, n = total() * channels(); i < n; ++i) p[i] += f;
+        return *this;
+    }
 
     uchar* data = nullptr;
     int rows = 0, cols = 0;
@@ -263,10 +283,64 @@ inline std::vector<std::vector<AreaEntry>> areaTab(int ssize, int dsize)
 }
 }  // namespace detail
 
+// INTER_CUBIC on CV_32F images (modules/imgproc/src/resize.cpp: interpolateCubic with A = -0.75, 4 taps, replicated border;
+// horizontal pass per source row, then vertical, all in fp32) -- what tensor_net.cpp:327 applies to the camera frame.
+namespace detail {
+struct CubicTap { int s[4]; float w[4]; };
+inline std::vector<CubicTap> cubicTab(int ssize, int dsize)
+{
+    const double scale = static_cast<double>(ssize) / dsize;
+    std::vector<CubicTap> tab(dsize);
+    for (int d = 0; d < dsize; ++d) {
+        float fx = static_cast<float>((d + 0.5) * scale - 0.5);
+        const int sx = static_cast<int>(std::floor(fx));
+        fx -= sx;
+        const float A = -0.75f;
+        CubicTap t;
+        t.w[0] = ((A * (fx + 1) - 5 * A) * (fx + 1) + 8 * A) * (fx + 1) - 4 * A;
+        t.w[1] = ((A + 2) * fx - (A + 3)) * fx * fx + 1;
+        t.w[2] = ((A + 2) * (1 - fx) - (A + 3)) * (1 - fx) * (1 - fx) + 1;
+        t.w[3] = 1.f - t.w[0] - t.w[1] - t.w[2];
+        for (int k = 0; k < 4; ++k) t.s[k] = std::min(std::max(sx - 1 + k, 0), ssize - 1);
+        tab[d] = t;
+    }
+    return tab;
+}
+}  // namespace detail
+
+inline void resizeCubic(const Mat& src, Mat& dst, Size dsize)
+{
+    const int cn = src.channels(), sh = src.rows, dw = dsize.width, dh = dsize.height;
+    const auto xt = detail::cubicTab(src.cols, dw), yt = detail::cubicTab(sh, dh);
+    std::vector<float> tmp(static_cast<size_t>(sh) * dw * cn);
+    for (int y = 0; y < sh; ++y) {
+        const float* s = src.ptr<float>(y);
+        float* t = &tmp[static_cast<size_t>(y) * dw * cn];
+        for (int dx = 0; dx < dw; ++dx)
+            for (int c = 0; c < cn; ++c) {
+                const detail::CubicTap& k = xt[dx];
+                t[dx * cn + c] = s[k.s[0] * cn + c] * k.w[0] + s[k.s[1] * cn + c] * k.w[1] + s[k.s[2] * cn + c] * k.w[2] + s[k.s[3] * cn + c] * k.w[3];
+            }
+    }
+    Mat out;
+    out.create(dh, dw, src.type());
+    for (int dy = 0; dy < dh; ++dy) {
+        float* d = out.ptr<float>(dy);
+        const detail::CubicTap& t = yt[dy];
+        const float* r0 = &tmp[static_cast<size_t>(t.s[0]) * dw * cn];
+        const float* r1 = &tmp[static_cast<size_t>(t.s[1]) * dw * cn];
+        const float* r2 = &tmp[static_cast<size_t>(t.s[2]) * dw * cn];
+        const float* r3 = &tmp[static_cast<size_t>(t.s[3]) * dw * cn];
+        for (int i = 0; i < dw * cn; ++i) d[i] = r0[i] * t.w[0] + r1[i] * t.w[1] + r2[i] * t.w[2] + r3[i] * t.w[3];
+    }
+    dst = out;
+}
+
 inline void resize(const Mat& src, Mat& dst, Size dsize, double = 0, double = 0, int interpolation = INTER_LINEAR)
 {
+    if (interpolation == INTER_CUBIC && src.depth() == CV_32F) { resizeCubic(src, dst, dsize); return; }
     if (interpolation != INTER_AREA || src.depth() != CV_32F || dsize.width > src.cols || dsize.height > src.rows) {
-        std::fprintf(stderr, "opencv shim: only INTER_AREA down-scaling of CV_32F images is implemented\n");
+        std::fprintf(stderr, "opencv shim: only INTER_AREA down-scaling and INTER_CUBIC of CV_32F images are implemented\n");
         std::abort();
     }
     const int cn = src.channels(), sw = src.cols, sh = src.rows, dw = dsize.width, dh = dsize.height;
@@ -293,6 +367,16 @@ inline void resize(const Mat& src, Mat& dst, Size dsize, double = 0, double = 0,
 
 inline void cvtColor(const Mat& src, Mat& dst, int code)
 {
+    if ((code == CV_BGRA2BGR || code == CV_BGRA2RGB) && src.channels() == 4) {      // drop alpha (and swap R/B for BGRA2RGB)
+        Mat o;
+        o.create(src.rows, src.cols, CV_MAKETYPE(src.depth(), 3));
+        const size_t es4 = src.elemSize1(), n4 = src.total();
+        for (size_t i = 0; i < n4; ++i)
+            for (int c = 0; c < 3; ++c)
+                std::memcpy(o.data + (3 * i + c) * es4, src.data + (4 * i + (code == CV_BGRA2RGB ? 2 - c : c)) * es4, es4);
+        dst = o;
+        return;
+    }
     if (code != CV_BGR2RGB || src.channels() != 3) std::abort();
     Mat out;
     out.create(src.rows, src.cols, src.type());
