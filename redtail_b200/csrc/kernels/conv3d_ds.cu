@@ -8,7 +8,7 @@
 // the THREE output planes p+1, p, p-1 in one MMA: the weights of the three filter planes are stacked along GEMM-N
 // (N = 3 x 64 with [W_hi ; W_lo] rows, + N = 96 for the A_lo x W_hi product), so A is read once per 96 output columns, the
 // MMAs last 96 / 48 clk, and all 27 weight tiles (108 KB) stay resident in shared memory for the life of the CTA -- a pipeline
-// stage is just two 10 KB activation boxes (hi, lo), five stages deep.
+// stage is just two 10 KB activation boxes (hi, lo), four stages deep; two warps issue the MMAs of alternate stages.
 //
 //   job    = one 8 x 16 patch of output positions, ALL depth planes (persistent CTAs, static round-robin over the patches)
 //   stage  = input plane p, filter column dw: one TMA box [10 rows x 16 positions x 32 ch] per fp16 plane (hi, lo); the three
@@ -23,7 +23,7 @@
 //
 // Numerics: the sequence of products and of fp32 additions per output element is exactly the generic kernel's (filter plane,
 // then filter column, then filter row, then K-step; one chunk per (plane, column)), so the two kernels agree bit for bit --
-// tests/test_gpu_plugins.py::test_conv3d_depth_stationary_bitexact -- and the parity of the nets is unchanged.
+// tests/test_gpu_plugins.py::test_conv3d_depth_stationary -- and the parity of the nets is unchanged.
 #include <cstdlib>
 #include <cstring>
 #include <vector>

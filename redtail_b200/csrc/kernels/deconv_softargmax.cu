@@ -13,6 +13,7 @@
 //            (8 buffers): columns c = (ph * 2 + pw) * 4 + t_d hold the contribution of input plane i to the output planes
 //            2i + t_d (filter plane t_d = 0, 1, 2) at output parity (ph, pw) -- depth-stationary like conv3d_ds.cu, so the
 //            sub-pixel formulation needs 16 MMAs per plane instead of 32.  The 8 KB of weights stay resident in shared memory.
+//   issue    = two warps on alternate planes, each with its own ring slots and TMEM buffers (see conv3d_ds.cu)
 //   epilogue = 16 warps, one (ph, pw) output pixel per thread: plane 2i = T0(i) + T2(i-1) (carried in a register),
 //            plane 2i+1 = T1(i); + bias; online (max, sum, weighted sum) soft-argmin update; after the last plane one
 //            fp32 disparity per pixel is written.
