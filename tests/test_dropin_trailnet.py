@@ -50,7 +50,7 @@ def test_reference_tensor_net_end_to_end(tmp_path):
         raw, out = str(tmp_path / "frame.bin"), str(tmp_path / "probs.f32")
         fr["frames"][k].tofile(raw)
         h, w = fr["frames"][k].shape[:2]
-        r = subprocess.run([exe, "run", proto, model, raw, str(w), str(h), out], capture_output=True, text=True, timeout=300)
+        r = subprocess.run([exe, "run", proto, model, raw, str(w), str(h), out], capture_output=True, text=True, timeout=120)
         print(r.stdout[-500:], r.stderr[-1500:])
         assert r.returncode == 0
         got = np.fromfile(out, dtype=np.float32)
