@@ -46,9 +46,9 @@ $CXX -o "$OUT/nvstereo_sample_app" "$OUT/main.o" "$OUT"/*_net.o $LIB -lz
 CR=/root/reference/ros/packages/caffe_ros
 if [ -d "$CR" ]; then
   CXX17="${CXX:-g++} -std=c++17 -O1 -w"
-  $CXX17 $INC -I"$CR/include" -c "$CR/src/tensor_net.cpp" -o "$OUT/tensor_net.o"
-  $CXX17 $INC -I"$CR/include" -c "$CR/src/int8_calibrator.cpp" -o "$OUT/int8_calibrator.o"
-  $CXX17 $INC -I"$CR/include" -c "$ROOT/tools/dropin/trailnet_driver.cpp" -o "$OUT/trailnet_driver.o"
-  $CXX17 -o "$OUT/caffe_ros_trailnet" "$OUT/trailnet_driver.o" "$OUT/tensor_net.o" "$OUT/int8_calibrator.o" $LIB -lz
+  $CXX17 $INC -I"$CR/include" -c "$CR/src/tensor_net.cpp" -o "$OUT/caffe_ros_tensornet.o"          # (not *_net.o: that glob is the stereo builders)
+  $CXX17 $INC -I"$CR/include" -c "$CR/src/int8_calibrator.cpp" -o "$OUT/caffe_ros_int8calib.o"
+  $CXX17 $INC -I"$CR/include" -c "$ROOT/tools/dropin/trailnet_driver.cpp" -o "$OUT/caffe_ros_driver.o"
+  $CXX17 -o "$OUT/caffe_ros_trailnet" "$OUT/caffe_ros_driver.o" "$OUT/caffe_ros_tensornet.o" "$OUT/caffe_ros_int8calib.o" $LIB -lz
 fi
 echo "built: $OUT/nvstereo_tests $OUT/nvstereo_net_driver $OUT/nvstereo_sample_app $OUT/caffe_ros_trailnet"
